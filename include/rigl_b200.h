@@ -1,0 +1,173 @@
+/* rigl_b200 -- C ABI of the B200-native RigL hot path.
+ *
+ * The reference (google-research/rigl) is pure Python/TensorFlow and has no FFI
+ * of its own; these entry points are what a binding for its two hot paths
+ * would call.  Each declaration cites the reference interface it replaces
+ * (file:line into the reference tree).  Conventions:
+ *   - plain pointers and sizes only; every tensor is caller-owned DEVICE memory
+ *     (allocated by PyTorch in this repo); nothing is retained past a call
+ *     except by the explicit plan objects, which hold pointers, not ownership;
+ *   - every function returns 0 on success, a negative rigl_status otherwise;
+ *     rigl_last_error() gives the message (thread-local);
+ *   - launches go to the `stream` argument (a cudaStream_t passed as void*),
+ *     no host synchronisation inside, safe under CUDA-graph capture unless
+ *     stated;
+ *   - weights / masks / gradients are float32, flattened in the reference's own
+ *     layout: HWIO [kh,kw,Cin,Cout] for conv kernels, [in,out] for dense
+ *     (Cout fastest) -- the flat index IS the tie-break order of tf.nn.top_k.
+ *   - a mask is a bitmap: bit (i & 31) of word (i >> 5) <=> mask.flat[i] == 1;
+ *     word count = rigl_mask_words(n); bits >= n are zero.
+ */
+#ifndef RIGL_B200_H_
+#define RIGL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RIGL_API __attribute__((visibility("default")))
+#else
+#define RIGL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RIGL_OK = 0,
+  RIGL_ERR_INVALID_ARG = -1,
+  RIGL_ERR_CUDA = -2,
+  RIGL_ERR_WORKSPACE = -3,
+  RIGL_ERR_UNSUPPORTED = -4,
+  RIGL_ERR_DRIVER = -5
+} rigl_status;
+
+/* Library version (major*10000 + minor*100 + patch). */
+RIGL_API int rigl_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+RIGL_API const char* rigl_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+RIGL_API uint64_t rigl_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Mask bitmaps  (reference: the float32 `mask` variable of
+ * tf.contrib.model_pruning masked layers; rigl/sparse_utils.py:39-45,71-87)
+ * ---------------------------------------------------------------------- */
+/* Words (uint32) a bitmap of n bits occupies; padded to a multiple of 4 words. */
+RIGL_API int64_t rigl_mask_words(int64_t n);
+/* bits <- (src[i] != 0).  Replaces tf.assign(mask, new_mask), sparse_utils.py:359-362. */
+RIGL_API int rigl_mask_pack_f32(const float* src, int64_t n, uint32_t* bits, void* stream);
+/* dst[i] <- bit ? 1.0f : 0.0f.  Replaces reading the mask variable. */
+RIGL_API int rigl_mask_unpack_f32(const uint32_t* bits, int64_t n, float* dst, void* stream);
+/* *out_count_dev <- popcount(bits) (one int32 on the device).  Replaces
+ * reduce_sum(mask): sparse_utils.py:39-45, sparse_optimizers_base.py:286,
+ * imagenet_resnet/utils.py:83-90. */
+RIGL_API int rigl_mask_popcount(const uint32_t* bits, int64_t n, int32_t* out_count_dev, void* stream);
+/* dst[i] <- bit ? src[i] : 0  (dL/dweights = mask * dL/d(masked_weights)),
+ * the masked gradient the wrapped optimizer consumes; sparse_optimizers_base.py:480. */
+RIGL_API int rigl_apply_mask_f32(const float* src, const uint32_t* bits, int64_t n, float* dst,
+                        float scale, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Periodic mask update: drop (magnitude top-k) + grow (dense-gradient top-k)
+ * Replaces SparseSETOptimizerBase._get_update_op (sparse_optimizers_base.py:
+ * 276-343) together with generic_mask_update (:260-274, :523-538),
+ * get_grow_tensor (:355-400, :540-553) and reset_momentum (:345-353, :555-564)
+ * for ALL masked layers in one batched launch sequence.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  float* weights;            /* [n] in/out: grown entries are overwritten        */
+  const float* score_grow;   /* [n] dense dL/d(mask*w) (RigL) | U[0,1) (SET) | mask (Static) */
+  uint32_t* mask_bits;       /* [rigl_mask_words(n)] in/out                      */
+  const float* noise;        /* [n] added to |mask*w| before ranking, or NULL    */
+  float* slots[2];           /* optimizer slots reset at new connections, or NULL */
+  const float* grow_values;  /* [n] used by RIGL_GROW_TENSOR, else NULL          */
+  const float* score_drop;   /* [n] explicit drop scores (overrides |mask*w|+noise), or NULL:
+                                the `_get_update_op(score_drop, ...)` entry, base.py:276 */
+  int64_t n;                 /* elements, 1 <= n < 2^31                          */
+  int32_t n_prune_override;  /* >= 0: use this n_prune; -1: int32(float32(n_ones)*drop_fraction) */
+  int32_t reserved;
+} rigl_layer_desc;
+
+typedef enum {
+  RIGL_GROW_ZEROS = 0,       /* 'zeros'            base.py:372-373 */
+  RIGL_GROW_TENSOR = 1,      /* caller-supplied    (random_normal/uniform/initial_dist draws) */
+  RIGL_GROW_GRAD_SCALE = 2,  /* 'grad_scale_<d>'   base.py:542-545: g / d */
+  RIGL_GROW_GRAD_SIGN = 3    /* 'grad_sign_<d>'    base.py:546-549: sign(g) / d */
+} rigl_grow_mode;
+
+typedef struct rigl_mask_plan rigl_mask_plan;
+
+/* Builds the device-side layer table and block schedule for a fixed set of
+ * layers (pointers are captured).  Not capturable (allocates). */
+RIGL_API int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers, rigl_mask_plan** out);
+RIGL_API int rigl_mask_plan_destroy(rigl_mask_plan* plan);
+/* Caller-owned scratch needed by rigl_mask_update_run (device memory, 256B aligned). */
+RIGL_API size_t rigl_mask_plan_workspace_bytes(const rigl_mask_plan* plan);
+/* One full update of every layer in the plan.
+ *   drop_fraction : float32 value of self.drop_fraction for this step (host-computed,
+ *                   base.py:232-258); n_prune = int32(float32(n_ones) * drop_fraction).
+ *   acc_scale     : initial_acc_scale; slots[.] <- score_grow * acc_scale at new connections.
+ *   reinit_when_same : base.py:328-333 (SparseStaticOptimizer passes 1).
+ * Per-layer results (n_ones, n_prune, n_keep, ...) are left in the workspace;
+ * see rigl_mask_plan_read_stats. */
+RIGL_API int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
+                         float grow_divisor, float acc_scale, int reinit_when_same,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Copies 8 int32 per layer {n_ones, n_prune, n_keep, drop_candidates, grow_candidates,
+ * drop_bucket, grow_bucket, 0} to host (synchronises the stream). */
+RIGL_API int rigl_mask_plan_read_stats(const rigl_mask_plan* plan, const void* workspace,
+                              int32_t* out_host, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Masked weight operands (mask fused into the fp32 -> bf16 weight load)
+ * Replaces `masked_weights = mask * weights` of tf.contrib.model_pruning
+ * (call sites rigl/imagenet_resnet/pruning_layers.py:140-157, 223-233).
+ * ---------------------------------------------------------------------- */
+/* Bytes of the packed operand blob for a [taps, cin, cout] weight tensor. */
+RIGL_API size_t rigl_packed_weights_bytes(int taps, int cin, int cout);
+/* From HWIO fp32 weights + bitmap, writes the packed blob (256B-aligned sections):
+ *   w_fprop bf16 [taps][cout][cin_pad]  (K = cin contiguous)   B operand of fprop
+ *   w_dgrad bf16 [taps][cin][cout_pad]  (K = cout contiguous)  B operand of dgrad
+ *   tile_nnz u32 [taps][ceil(cout/64)][ceil(cin/64)]  surviving weights per 64x64
+ *            weight tile -- the per-tile gate: all-zero tiles are never fetched.
+ * cin_pad / cout_pad = rounded up to a multiple of 8 (16-byte rows); padding = 0. */
+RIGL_API int rigl_pack_masked_weights(const float* w_hwio, const uint32_t* mask_bits, int taps,
+                                      int cin, int cout, void* packed, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Masked conv2d / linear as implicit GEMM (tcgen05 on sm_100a; a CUDA-core
+ * kernel serves shapes whose row pitch is not a 16-byte multiple).
+ * Replaces layers.masked_conv2d / masked_fully_connected fprop and its two
+ * gradient GEMMs (pruning_layers.py:72-172, 175-248; sparse_optimizers_base.py:
+ * 478-485 for the dense wgrad RigL needs).
+ * Activations: NHWC bf16.  Square kernels and strides (pruning_layers.py:143-144).
+ * A dense layer is the 1x1 case with in_h = in_w = 1 and batch = rows.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, in_h, in_w, cin;     /* x  [batch,in_h,in_w,cin]   bf16 NHWC */
+  int32_t out_h, out_w, cout;         /* y  [batch,out_h,out_w,cout] bf16 NHWC */
+  int32_t ksize, stride, pad;         /* square; pad = (ksize-1)/2 (resnet_model.py:83-108,278-281) */
+} rigl_conv_desc;
+
+RIGL_API size_t rigl_conv_workspace_bytes(const rigl_conv_desc* d);
+/* y = conv(x, mask*W) (+ bias[cout]).  `packed` from rigl_pack_masked_weights.
+ * y_bf16 and/or y_f32 receive the result (either may be NULL, not both). */
+RIGL_API int rigl_masked_conv2d_fprop(const rigl_conv_desc* d, const void* x, const void* packed,
+                                      void* y_bf16, float* y_f32, const float* bias, void* ws,
+                                      size_t ws_bytes, void* stream);
+/* dx = conv^T(dy, mask*W). */
+RIGL_API int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, const void* packed,
+                                      void* dx, void* ws, size_t ws_bytes, void* stream);
+/* dw[kh,kw,cin,cout] (fp32, HWIO, DENSE -- every position, as RigL's grow needs)
+ * = sum over pixels x (x) dy.  beta=0 overwrites, beta=1 accumulates into dw. */
+RIGL_API int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, const void* dy,
+                                     float* dw, float beta, void* ws, size_t ws_bytes, void* stream);
+/* 1 to route every conv call through the CUDA-core kernels (debug cross-check). */
+RIGL_API int rigl_set_force_simt(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RIGL_B200_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI in include/rigl_b200.h.
+
+There is no CPU fallback: if librigl_b200.so is missing, `lib()` raises with
+the build command.  Tensors are passed as raw device pointers (`data_ptr()`),
+streams as the integer `cudaStream_t` of torch's current stream.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librigl_b200.so')
+_lib = None
+
+
+class RiglError(RuntimeError):
+  pass
+
+
+class LayerDesc(C.Structure):
+  _fields_ = [('weights', C.c_void_p), ('score_grow', C.c_void_p), ('mask_bits', C.c_void_p),
+              ('noise', C.c_void_p), ('slots', C.c_void_p * 2), ('grow_values', C.c_void_p), ('score_drop', C.c_void_p),
+              ('n', C.c_int64), ('n_prune_override', C.c_int32), ('reserved', C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+  _fields_ = [('batch', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('cin', C.c_int32),
+              ('out_h', C.c_int32), ('out_w', C.c_int32), ('cout', C.c_int32),
+              ('ksize', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32)]
+
+
+GROW_ZEROS, GROW_TENSOR, GROW_GRAD_SCALE, GROW_GRAD_SIGN = 0, 1, 2, 3
+
+_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/rigl_b200.h declares.
+SIGNATURES = {
+    'rigl_version': (C.c_int, []),
+    'rigl_last_error': (C.c_char_p, []),
+    'rigl_launch_count': (C.c_uint64, []),
+    'rigl_mask_words': (_i64, [_i64]),
+    'rigl_mask_pack_f32': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'rigl_mask_unpack_f32': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'rigl_mask_popcount': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'rigl_apply_mask_f32': (C.c_int, [_vp, _vp, _i64, _vp, _f32, _vp]),
+    'rigl_mask_plan_create': (C.c_int, [C.POINTER(LayerDesc), _i32, C.POINTER(_vp)]),
+    'rigl_mask_plan_destroy': (C.c_int, [_vp]),
+    'rigl_mask_plan_workspace_bytes': (_sz, [_vp]),
+    'rigl_mask_update_run': (C.c_int, [_vp, _f32, _i32, _f32, _f32, _i32, _vp, _sz, _vp]),
+    'rigl_mask_plan_read_stats': (C.c_int, [_vp, _vp, C.POINTER(C.c_int32), _vp]),
+    'rigl_packed_weights_bytes': (_sz, [_i32, _i32, _i32]),
+    'rigl_pack_masked_weights': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'rigl_conv_workspace_bytes': (_sz, [C.POINTER(ConvDesc)]),
+    'rigl_masked_conv2d_fprop': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'rigl_masked_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    'rigl_conv2d_wgrad_dense': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
+    'rigl_set_force_simt': (C.c_int, [_i32]),
+}
+
+
+def lib():
+  """Loads (once) and returns the ctypes handle; fails loudly if absent."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RiglError('librigl_b200.so not built: run `python -m rigl_b200.build` '
+                      '(or __graft_entry__.build()); there is no CPU fallback')
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+      fn = getattr(handle, name)
+      fn.restype = res
+      fn.argtypes = args
+    _lib = handle
+  return _lib
+
+
+def check(status, what=''):
+  if status != 0:
+    msg = lib().rigl_last_error().decode('utf-8', 'replace')
+    raise RiglError('%s failed (%d): %s' % (what or 'rigl call', status, msg))
+
+
+def stream_ptr():
+  import torch
+  return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+  return int(lib().rigl_launch_count())

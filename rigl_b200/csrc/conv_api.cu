@@ -1,0 +1,88 @@
+// C-ABI entry points of the masked conv / linear path: argument validation and
+// the shape dispatch between the tcgen05 implicit-GEMM kernels (igemm_tc.cu)
+// and the CUDA-core kernels (conv_simt.cu).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace rigl {
+
+static int g_force_simt = -1;
+
+static bool force_simt() {
+  if (g_force_simt < 0) {
+    const char* e = getenv("RIGL_FORCE_SIMT");
+    g_force_simt = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_force_simt == 1;
+}
+
+int geom_from_desc(const rigl_conv_desc* d, ConvGeom* g) {
+  RIGL_REQUIRE(d != nullptr, "null conv desc");
+  RIGL_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cin > 0 && d->cout > 0 && d->ksize > 0 &&
+                   d->stride > 0 && d->pad >= 0,
+               "conv desc: non-positive dimension");
+  const int eh = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
+  const int ew = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
+  RIGL_REQUIRE(d->out_h == eh && d->out_w == ew, "conv desc: out %dx%d inconsistent (expected %dx%d)",
+               d->out_h, d->out_w, eh, ew);
+  g->batch = d->batch; g->in_h = d->in_h; g->in_w = d->in_w; g->cin = d->cin;
+  g->out_h = d->out_h; g->out_w = d->out_w; g->cout = d->cout;
+  g->ksize = d->ksize; g->stride = d->stride; g->pad = d->pad;
+  g->cin_pad = round_up8(d->cin); g->cout_pad = round_up8(d->cout);
+  return RIGL_OK;
+}
+
+}  // namespace rigl
+
+using namespace rigl;
+
+extern "C" int rigl_set_force_simt(int on) {
+  g_force_simt = on ? 1 : 0;
+  return RIGL_OK;
+}
+
+extern "C" size_t rigl_conv_workspace_bytes(const rigl_conv_desc* d) {
+  ConvGeom g;
+  if (geom_from_desc(d, &g) != RIGL_OK) return 0;
+  return tc_workspace_bytes(g);
+}
+
+extern "C" int rigl_masked_conv2d_fprop(const rigl_conv_desc* d, const void* x, const void* packed,
+                                        void* y_bf16, float* y_f32, const float* bias, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && packed && (y_bf16 || y_f32), "rigl_masked_conv2d_fprop: null tensor");
+  const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
+  if (!force_simt() && tc_supported(g, 0))
+    return tc_fprop(g, x, packed, y_bf16, y_f32, bias, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_fprop(g, x, static_cast<const uint8_t*>(packed) + L.off_dgrad, y_bf16, y_f32, bias,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, const void* packed,
+                                        void* dx, void* ws, size_t ws_bytes, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(dy && packed && dx, "rigl_masked_conv2d_dgrad: null tensor");
+  const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
+  if (!force_simt() && tc_supported(g, 1))
+    return tc_dgrad(g, dy, packed, dx, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_dgrad(g, dy, static_cast<const uint8_t*>(packed) + L.off_fprop, dx, (cudaStream_t)stream);
+}
+
+extern "C" int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, const void* dy, float* dw,
+                                       float beta, void* ws, size_t ws_bytes, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && dy && dw, "rigl_conv2d_wgrad_dense: null tensor");
+  RIGL_REQUIRE(beta == 0.f || beta == 1.f, "rigl_conv2d_wgrad_dense: beta must be 0 or 1");
+  if (!force_simt() && tc_supported(g, 2))
+    return tc_wgrad(g, x, dy, dw, beta, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_wgrad(g, x, dy, dw, beta, (cudaStream_t)stream);
+}

@@ -1,0 +1,310 @@
+"""Masked conv2d / fully-connected layers on the CUDA hot path.
+
+Mirror of the reference's masked-layer shim rigl/imagenet_resnet/pruning_layers.py
+(sparse_conv2d :72-172, sparse_fully_connected :175-248), which delegates to
+tf.contrib.model_pruning's masked_conv2d / masked_fully_connected:
+  y = conv(x, mask * W) (+ bias)     weights HWIO [kh,kw,Cin,Cout] / [in,out] float32
+Each layer owns
+  .weight           float32 Parameter in the reference layout, `.name` '<scope>/weights:0'
+  .mask             MaskVariable (1-bit bitmap), `.name` '<scope>/mask:0'
+  .masked_weights   handle whose `.dense_grad` receives dL/d(mask*W) -- the DENSE
+                    gradient RigL ranks for regrowth (sparse_optimizers_base.py:481-484)
+and registers itself in `rigl_b200.pruning` (the graph-collection analogue).
+Activations are bf16 NHWC: conv inputs are torch tensors of logical shape
+[N,C,H,W] in `torch.channels_last` memory format.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi
+from . import pruning
+from .masks import MaskVariable
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+  ws = _WS.get(device)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+    _WS[device] = ws
+  return ws
+
+
+class MaskedWeights(object):
+  """Handle for `mask * weights`; carries the dense gradient buffer."""
+
+  def __init__(self, scope, numel, device):
+    self.name = scope + '/masked_weights:0'
+    self.dense_grad = torch.zeros(numel, dtype=torch.float32, device=device)
+    self.fresh = False        # True once a backward has written dense_grad this step
+
+
+def variance_scaling_(tensor_hwio, scale=2.0):
+  """fan_in variance scaling on an HWIO / [in,out] tensor (resnet_model.py:283 uses
+  tf.variance_scaling_initializer; a plain normal is used here -- only the
+  synthetic weight distribution depends on it, not parity)."""
+  fan_in = int(np.prod(tensor_hwio.shape[:-1]))
+  with torch.no_grad():
+    tensor_hwio.normal_(0., math.sqrt(scale / max(fan_in, 1)))
+  return tensor_hwio
+
+
+class _MaskedConvFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, weight, bias, layer, out_f32):
+    layer.pack()
+    y = layer._fprop(x, bias, out_f32)
+    ctx.layer = layer
+    ctx.save_for_backward(x)
+    ctx.has_bias = bias is not None
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    layer = ctx.layer
+    x, = ctx.saved_tensors
+    dy16 = layer._as_activation(dy, layer.out_channels)
+    dx = layer._dgrad(dy16, x) if ctx.needs_input_grad[0] else None
+    mw = layer.masked_weights
+    layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh)
+    mw.fresh = True
+    gw = None
+    if ctx.needs_input_grad[1]:
+      gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
+    gb = None
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      gb = dy.float().reshape(-1, layer.out_channels).sum(0) if dy.dim() == 2 else \
+          dy.float().sum(dim=(0, 2, 3))
+    return dx, gw, gb, None, None
+
+
+class _MaskedLayer(nn.Module):
+  is_rigl_masked_layer = True
+
+  def _setup(self, scope, shape_hwio, device, registry, kernel_initializer):
+    self.scope = scope
+    w = torch.empty(shape_hwio, dtype=torch.float32, device=device)
+    (kernel_initializer or variance_scaling_)(w)
+    self.weight = nn.Parameter(w)
+    self.weight.name = scope + '/weights:0'
+    self.mask = MaskVariable(scope, shape_hwio, device)
+    self.masked_weights = MaskedWeights(scope, w.numel(), device)
+    taps = int(np.prod(shape_hwio[:-2])) if len(shape_hwio) > 2 else 1
+    self._taps, self._cin, self._cout = taps, int(shape_hwio[-2]), int(shape_hwio[-1])
+    nbytes = int(_cabi.lib().rigl_packed_weights_bytes(taps, self._cin, self._cout))
+    self.packed = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    (registry if registry is not None else pruning.default_registry()).register(self)
+
+  @property
+  def in_channels(self):
+    return self._cin
+
+  @property
+  def out_channels(self):
+    return self._cout
+
+  def pack(self):
+    """mask * W -> bf16 GEMM operands (both K-major layouts) + tile survivor counts."""
+    _cabi.check(_cabi.lib().rigl_pack_masked_weights(
+        self.weight.data_ptr(), self.mask.bits.data_ptr(), self._taps, self._cin, self._cout,
+        self.packed.data_ptr(), _cabi.stream_ptr()), 'rigl_pack_masked_weights')
+
+  def extra_repr(self):
+    return '%s, hwio=%s' % (self.scope, tuple(self.weight.shape))
+
+
+class SparseConv2d(_MaskedLayer):
+  """Masked 2-D convolution, square kernel/stride, no bias (resnet_model.py:296)."""
+
+  def __init__(self, in_channels, units, kernel_size, strides=1, padding='SAME', name=None,
+               kernel_initializer=None, device='cuda', registry=None):
+    super(SparseConv2d, self).__init__()
+    k = int(kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size)
+    s = int(strides[0] if isinstance(strides, (tuple, list)) else strides)
+    if padding not in ('SAME', 'VALID'):
+      raise ValueError('padding must be SAME or VALID')
+    self.ksize, self.stride = k, s
+    # conv2d_fixed_padding (resnet_model.py:234-303): explicit (k-1)//2 pad then VALID for
+    # stride>1; SAME for stride 1 -- both are a symmetric pad of (k-1)//2 for odd k.
+    self.pad = (k - 1) // 2 if padding == 'SAME' else 0
+    self._setup(name or 'Conv', (k, k, int(in_channels), int(units)), device, registry,
+                kernel_initializer)
+
+  def _desc(self, n, h, w):
+    d = _cabi.ConvDesc()
+    d.batch, d.in_h, d.in_w, d.cin = n, h, w, self._cin
+    d.out_h = (h + 2 * self.pad - self.ksize) // self.stride + 1
+    d.out_w = (w + 2 * self.pad - self.ksize) // self.stride + 1
+    d.cout, d.ksize, d.stride, d.pad = self._cout, self.ksize, self.stride, self.pad
+    return d
+
+  @staticmethod
+  def _as_activation(t, channels):
+    if t.dtype != torch.bfloat16:
+      t = t.to(torch.bfloat16)
+    return t.contiguous(memory_format=torch.channels_last)
+
+  def _fprop(self, x, bias, out_f32):
+    n, c, h, w = x.shape
+    d = self._desc(n, h, w)
+    y = torch.empty((n, self._cout, d.out_h, d.out_w), dtype=torch.bfloat16, device=x.device,
+                    memory_format=torch.channels_last)
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    _cabi.check(_cabi.lib().rigl_masked_conv2d_fprop(
+        d, x.data_ptr(), self.packed.data_ptr(), y.data_ptr(), None, None, ws.data_ptr(),
+        ws.numel(), _cabi.stream_ptr()), 'rigl_masked_conv2d_fprop')
+    return y
+
+  def _dgrad(self, dy, x):
+    n, c, h, w = x.shape
+    d = self._desc(n, h, w)
+    dx = torch.empty_like(x, memory_format=torch.channels_last)
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    _cabi.check(_cabi.lib().rigl_masked_conv2d_dgrad(
+        d, dy.data_ptr(), self.packed.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(),
+        _cabi.stream_ptr()), 'rigl_masked_conv2d_dgrad')
+    return dx
+
+  def _wgrad(self, x, dy, out, accumulate):
+    n, c, h, w = x.shape
+    d = self._desc(n, h, w)
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    _cabi.check(_cabi.lib().rigl_conv2d_wgrad_dense(
+        d, x.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
+        ws.numel(), _cabi.stream_ptr()), 'rigl_conv2d_wgrad_dense')
+
+  def forward(self, x):
+    if x.dim() != 4:
+      raise ValueError('Rank not supported {}'.format(x.dim()))
+    if x.shape[1] != self._cin:
+      raise ValueError('expected %d input channels, got %d' % (self._cin, x.shape[1]))
+    x = self._as_activation(x, self._cin)
+    return _MaskedConvFn.apply(x, self.weight, None, self, False)
+
+
+class SparseLinear(_MaskedLayer):
+  """Masked fully-connected layer, weights [in,out], dense zero-init bias."""
+
+  def __init__(self, in_features, units, use_bias=True, name=None, kernel_initializer=None,
+               device='cuda', registry=None, out_dtype=torch.bfloat16):
+    super(SparseLinear, self).__init__()
+    self.ksize, self.stride, self.pad = 1, 1, 0
+    self.out_dtype = out_dtype
+    self._setup(name or 'Dense', (int(in_features), int(units)), device, registry,
+                kernel_initializer)
+    if use_bias:
+      self.bias = nn.Parameter(torch.zeros(int(units), dtype=torch.float32, device=device))
+      self.bias.name = self.scope + '/biases:0'
+    else:
+      self.register_parameter('bias', None)
+
+  def _desc(self, m):
+    d = _cabi.ConvDesc()
+    d.batch, d.in_h, d.in_w, d.cin = m, 1, 1, self._cin
+    d.out_h, d.out_w, d.cout, d.ksize, d.stride, d.pad = 1, 1, self._cout, 1, 1, 0
+    return d
+
+  @staticmethod
+  def _as_activation(t, channels):
+    t = t.reshape(-1, channels)
+    if t.dtype != torch.bfloat16:
+      t = t.to(torch.bfloat16)
+    return t.contiguous()
+
+  def _fprop(self, x, bias, out_f32):
+    d = self._desc(x.shape[0])
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    y16 = None if out_f32 else torch.empty((x.shape[0], self._cout), dtype=torch.bfloat16, device=x.device)
+    y32 = torch.empty((x.shape[0], self._cout), dtype=torch.float32, device=x.device) if out_f32 else None
+    _cabi.check(_cabi.lib().rigl_masked_conv2d_fprop(
+        d, x.data_ptr(), self.packed.data_ptr(), None if y16 is None else y16.data_ptr(),
+        None if y32 is None else y32.data_ptr(), None if bias is None else bias.data_ptr(),
+        ws.data_ptr(), ws.numel(), _cabi.stream_ptr()), 'rigl_masked_conv2d_fprop')
+    return y32 if out_f32 else y16
+
+  def _dgrad(self, dy, x):
+    d = self._desc(x.shape[0])
+    dx = torch.empty_like(x)
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    _cabi.check(_cabi.lib().rigl_masked_conv2d_dgrad(
+        d, dy.data_ptr(), self.packed.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(),
+        _cabi.stream_ptr()), 'rigl_masked_conv2d_dgrad')
+    return dx
+
+  def _wgrad(self, x, dy, out, accumulate):
+    d = self._desc(x.shape[0])
+    ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    _cabi.check(_cabi.lib().rigl_conv2d_wgrad_dense(
+        d, x.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
+        ws.numel(), _cabi.stream_ptr()), 'rigl_conv2d_wgrad_dense')
+
+  def forward(self, x):
+    lead = x.shape[:-1]
+    x2 = self._as_activation(x, self._cin)
+    y = _MaskedConvFn.apply(x2, self.weight, self.bias, self, self.out_dtype == torch.float32)
+    return y.reshape(*lead, self._cout)
+
+
+# ---- functional, reference-signature entry points (variable-scope style reuse) ----
+_SCOPED = {}
+
+
+def reset_scopes():
+  _SCOPED.clear()
+
+
+def sparse_conv2d(x, units, kernel_size, activation=None, use_bias=False, kernel_initializer=None,
+                  kernel_regularizer=None, bias_initializer=None, biases_regularizer=None,
+                  sparsity_technique='baseline', normalizer_fn=None, strides=(1, 1), padding='SAME',
+                  data_format='channels_last', name=None):
+  """Reference-signature conv (pruning_layers.py:72-86).  `x` is a 4-D bf16 tensor of
+  logical shape [N,C,H,W] (channels_last memory = NHWC).  The layer object is created
+  on first use of `name` and reused afterwards (variable_scope reuse semantics)."""
+  if data_format not in ('channels_last', 'channels_first'):
+    raise ValueError('Not a valid channel string:', data_format)
+  if x.dim() != 4:
+    raise ValueError('Rank not supported {}'.format(x.dim()))
+  key = ('conv', name)
+  layer = _SCOPED.get(key) if name else None
+  if layer is None:
+    if sparsity_technique == 'threshold':
+      layer = SparseConv2d(x.shape[1], units, kernel_size, strides=strides, padding=padding,
+                           name=name, kernel_initializer=kernel_initializer, device=x.device)
+    elif sparsity_technique == 'baseline':
+      k = kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size
+      s = strides[0] if isinstance(strides, (tuple, list)) else strides
+      layer = nn.Conv2d(x.shape[1], units, k, stride=s, padding=(k - 1) // 2 if padding == 'SAME' else 0,
+                        bias=use_bias, device=x.device, dtype=x.dtype)
+    else:
+      raise ValueError('Unsupported sparsity technique {}'.format(sparsity_technique))
+    if name:
+      _SCOPED[key] = layer
+  y = layer(x)
+  if normalizer_fn is not None:
+    y = normalizer_fn(y)
+  return activation(y) if activation is not None else y
+
+
+def sparse_fully_connected(x, units, activation=None, use_bias=True, kernel_initializer=None,
+                           kernel_regularizer=None, bias_initializer=None, biases_regularizer=None,
+                           sparsity_technique='baseline', name=None):
+  """Reference-signature dense layer (pruning_layers.py:175-184)."""
+  key = ('dense', name)
+  layer = _SCOPED.get(key) if name else None
+  if layer is None:
+    if sparsity_technique == 'threshold':
+      layer = SparseLinear(x.shape[-1], units, use_bias=use_bias, name=name,
+                           kernel_initializer=kernel_initializer, device=x.device)
+    elif sparsity_technique == 'baseline':
+      layer = nn.Linear(x.shape[-1], units, bias=use_bias, device=x.device, dtype=x.dtype)
+    else:
+      raise ValueError('Unsupported sparsity technique {}'.format(sparsity_technique))
+    if name:
+      _SCOPED[key] = layer
+  y = layer(x)
+  return activation(y) if activation is not None else y

@@ -1,0 +1,258 @@
+"""Parity of the batched CUDA mask update with the CPU oracle: mask indices,
+re-initialised weights and optimizer slots must be BIT-IDENTICAL (integer /
+index work; tolerance = 0)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rigl_oracle as orc
+from rigl_b200 import _cabi
+from rigl_b200.masks import MaskUpdateEngine, MaskVariable
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _t(a):
+  return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+
+
+def _run_case(layers_np, drop_fraction, grow_mode=_cabi.GROW_ZEROS, grow_divisor=1.0, acc_scale=0.0,
+              reinit=False, check_stats=True):
+  """layers_np: list of dicts(mask, w, g, noise?, slots?, grow_values?, score_drop?, n_prune?)."""
+  eng = MaskUpdateEngine()
+  specs, keep = [], []
+  for i, ly in enumerate(layers_np):
+    mv = MaskVariable('layer%d' % i, ly['mask'].shape, DEV)
+    mv.assign(ly['mask'])
+    w, g = _t(ly['w']).view(-1), _t(ly['g']).view(-1)
+    spec = dict(mask=mv, weights=w, score_grow=g)
+    if ly.get('noise') is not None:
+      spec['noise'] = _t(ly['noise']).view(-1)
+    if ly.get('slots'):
+      spec['slots'] = [_t(s).view(-1) for s in ly['slots']]
+    if ly.get('grow_values') is not None:
+      spec['grow_values'] = _t(ly['grow_values']).view(-1)
+    if ly.get('score_drop') is not None:
+      spec['score_drop'] = _t(ly['score_drop']).view(-1)
+    if 'n_prune' in ly:
+      spec['n_prune'] = ly['n_prune']
+    specs.append(spec)
+  eng.run(specs, np.float32(drop_fraction), grow_mode=grow_mode, grow_divisor=grow_divisor,
+          acc_scale=acc_scale, reinit_when_same=reinit)
+  torch.cuda.synchronize()
+  stats = eng.stats()
+  for i, (ly, spec) in enumerate(zip(layers_np, specs)):
+    m, w, g = ly['mask'], ly['w'], ly['g']
+    if ly.get('score_drop') is not None:
+      sd = ly['score_drop'].astype(np.float32)
+    else:
+      sd = np.abs(m.astype(np.float32) * w.astype(np.float32))
+      if ly.get('noise') is not None:
+        sd = (sd + ly['noise'].astype(np.float32)).astype(np.float32)
+    sg = np.abs(g.astype(np.float32))
+    if grow_mode == _cabi.GROW_ZEROS:
+      grow = None
+    elif grow_mode == _cabi.GROW_TENSOR:
+      grow = ly['grow_values']
+    elif grow_mode == _cabi.GROW_GRAD_SCALE:
+      grow = (g.astype(np.float32) / np.float32(grow_divisor)).astype(np.float32)
+    else:
+      grow = (np.sign(g.astype(np.float32)) / np.float32(grow_divisor)).astype(np.float32)
+    frac = drop_fraction
+    if 'n_prune' in ly:      # emulate the override through an exact fraction-free path
+      n_ones = int(m.sum())
+      frac = None
+    if frac is None:
+      want = _oracle_with_n_prune(sd, sg, m, w, ly['n_prune'], grow, reinit, ly.get('slots') or [],
+                                  (g.astype(np.float32) * np.float32(acc_scale)).astype(np.float32))
+    else:
+      want = orc.get_update_op(sd, sg, m, w, frac, grow_tensor=grow, reinit_when_same=reinit,
+                               slots=ly.get('slots') or [],
+                               slot_reset=(g.astype(np.float32) * np.float32(acc_scale)).astype(np.float32))
+    got_mask = spec['mask'].numpy()
+    assert np.array_equal(got_mask, want['mask']), 'layer %d mask differs at %d positions' % (
+        i, int((got_mask != want['mask']).sum()))
+    got_w = spec['weights'].cpu().numpy().reshape(w.shape)
+    assert got_w.tobytes() == want['weights'].astype(np.float32).tobytes(), 'layer %d weights' % i
+    for s_got, s_want in zip(spec.get('slots', []), want['slots']):
+      assert s_got.cpu().numpy().reshape(w.shape).tobytes() == s_want.astype(np.float32).tobytes()
+    if check_stats:
+      assert stats[i][0] == int(m.sum()) and stats[i][1] == want['n_prune'] and stats[i][2] == want['n_keep']
+  return stats
+
+
+def _oracle_with_n_prune(sd, sg, m, w, n_prune, grow, reinit, slots, slot_reset):
+  n_ones = int(m.sum())
+  if n_ones == 0:
+    frac = 0.0
+  else:
+    # find a float32 fraction reproducing n_prune exactly
+    frac = None
+    for cand in (np.float32(n_prune / n_ones), np.nextafter(np.float32(n_prune / n_ones), np.float32(2)),
+                 np.float32((n_prune + 0.5) / n_ones)):
+      if int(np.int32(np.float32(n_ones) * np.float32(cand))) == n_prune:
+        frac = cand
+        break
+    assert frac is not None
+  return orc.get_update_op(sd, sg, m, w, frac, grow_tensor=grow, reinit_when_same=reinit, slots=slots,
+                           slot_reset=slot_reset)
+
+
+def _layer(rng, shape, sparsity, noise_std=0., slots=0):
+  w = rng.standard_normal(shape).astype(np.float32) * np.float32(0.05)
+  g = rng.standard_normal(shape).astype(np.float32) * np.float32(1e-3)
+  m = orc.get_mask_random_numpy(shape, sparsity, rng).astype(np.float32)
+  ly = dict(mask=m, w=w, g=g)
+  if noise_std:
+    ly['noise'] = (rng.standard_normal(shape) * noise_std).astype(np.float32)
+  if slots:
+    ly['slots'] = [rng.standard_normal(shape).astype(np.float32) for _ in range(slots)]
+  return ly
+
+
+def test_mnist_layers_no_noise():
+  rng = np.random.RandomState(0)
+  layers = [_layer(rng, (784, 300), 0.9, slots=1), _layer(rng, (300, 100), 0.81, slots=1),
+            _layer(rng, (100, 10), 0.0, slots=1)]
+  _run_case(layers, 0.3)
+
+
+def test_mnist_layers_injected_noise_and_acc_scale():
+  rng = np.random.RandomState(1)
+  layers = [_layer(rng, (784, 300), 0.9, noise_std=1e-5, slots=1),
+            _layer(rng, (300, 100), 0.81, noise_std=1e-5, slots=2),
+            _layer(rng, (100, 10), 0.0, noise_std=1e-5)]
+  _run_case(layers, 0.2999, acc_scale=0.5)
+
+
+@pytest.mark.parametrize('n', [1, 2, 5, 31, 32, 33, 127, 128, 129, 1000, 4097, 32768, 32769, 70001])
+def test_ragged_sizes(n):
+  rng = np.random.RandomState(n)
+  _run_case([_layer(rng, (n,), 0.5, slots=1)], 0.37)
+
+
+@pytest.mark.parametrize('frac', [0.0, 1.0, 0.5, 1e-9, 0.999999])
+def test_extreme_fractions(frac):
+  rng = np.random.RandomState(7)
+  _run_case([_layer(rng, (3, 3, 16, 32), 0.8, slots=1), _layer(rng, (257,), 0.3)], frac)
+
+
+def test_all_zero_scores_tie_break_by_index():
+  # every drop score is exactly 0 and every grow score equal: pure index tie-break,
+  # inactive positions outrank higher-index active ones (SURVEY hard part 4).
+  n = 50000
+  rng = np.random.RandomState(3)
+  m = (rng.rand(n) < 0.3).astype(np.float32)
+  ly = dict(mask=m, w=np.zeros(n, np.float32), g=np.full(n, 0.25, np.float32),
+            slots=[np.ones(n, np.float32)])
+  _run_case([ly], 0.4)
+
+
+def test_heavy_duplicates():
+  rng = np.random.RandomState(4)
+  n = 200000
+  m = (rng.rand(n) < 0.2).astype(np.float32)
+  w = (rng.randint(-3, 4, n) * 0.125).astype(np.float32)        # 7 distinct values incl. 0
+  g = (rng.randint(-2, 3, n) * 0.5).astype(np.float32)
+  _run_case([dict(mask=m, w=w, g=g, slots=[rng.standard_normal(n).astype(np.float32)])], 0.3)
+
+
+def test_negative_zero_and_negative_noise():
+  n = 4096
+  rng = np.random.RandomState(5)
+  m = (rng.rand(n) < 0.5).astype(np.float32)
+  w = rng.standard_normal(n).astype(np.float32) * 1e-6
+  w[::7] = -0.0
+  g = rng.standard_normal(n).astype(np.float32)
+  g[::5] = -0.0
+  noise = (rng.standard_normal(n) * 1e-5).astype(np.float32)     # scores go negative
+  _run_case([dict(mask=m, w=w, g=g, noise=noise)], 0.3)
+
+
+def test_all_ones_and_all_zeros_masks():
+  rng = np.random.RandomState(6)
+  a = _layer(rng, (100, 10), 0.0, slots=1)
+  b = _layer(rng, (64, 64), 0.5)
+  b['mask'][:] = 0
+  _run_case([a, b], 0.3)
+
+
+@pytest.mark.parametrize('mode,div', [(_cabi.GROW_GRAD_SCALE, 2.0), (_cabi.GROW_GRAD_SIGN, 4.0),
+                                      (_cabi.GROW_TENSOR, 1.0)])
+def test_grow_init_modes(mode, div):
+  rng = np.random.RandomState(8)
+  ly = _layer(rng, (3, 3, 32, 32), 0.85, slots=1)
+  ly['g'][0, 0, 0, :5] = 0.0
+  if mode == _cabi.GROW_TENSOR:
+    ly['grow_values'] = rng.standard_normal(ly['w'].shape).astype(np.float32)
+  _run_case([ly], 0.3, grow_mode=mode, grow_divisor=div, acc_scale=0.1)
+
+
+def test_reinit_when_same_static_flavour():
+  # SparseStaticOptimizer: grow score = mask, reinit_when_same (sparse_optimizers.py:109-123)
+  rng = np.random.RandomState(9)
+  ly = _layer(rng, (128, 64), 0.7, slots=1)
+  ly['g'] = ly['mask'].copy()
+  ly['grow_values'] = rng.standard_normal(ly['w'].shape).astype(np.float32)
+  before = ly['mask'].copy()
+  _run_case([ly], 0.3, grow_mode=_cabi.GROW_TENSOR, reinit=True)
+  # (mask unchanged is asserted through oracle equality; double-check the invariant itself)
+  want = orc.get_update_op(np.abs(before * ly['w']), before, before, ly['w'], 0.3,
+                           grow_tensor=ly['grow_values'], reinit_when_same=True)
+  assert np.array_equal(want['mask'], before)
+
+
+def test_explicit_score_drop_entry():
+  rng = np.random.RandomState(10)
+  ly = _layer(rng, (500, 40), 0.6)
+  ly['score_drop'] = rng.standard_normal(ly['w'].shape).astype(np.float32)     # arbitrary, incl. negative
+  _run_case([ly], 0.25)
+
+
+def test_n_prune_override():
+  rng = np.random.RandomState(11)
+  ly = _layer(rng, (1000,), 0.5)
+  ly['n_prune'] = 123
+  _run_case([ly], 0.9, check_stats=False)
+
+
+def test_set_flavour_uniform_scores():
+  rng = np.random.RandomState(12)
+  ly = _layer(rng, (15, 25), 0.5, slots=1)
+  ly['g'] = rng.rand(15, 25).astype(np.float32)
+  _run_case([ly], 0.5)
+
+
+def test_wrn22_2_layer_set(golden):
+  case = [c for c in golden['cases'] if c['tag'] == 'wrn22_2_erk95'][0]
+  rng = np.random.RandomState(13)
+  layers = [_layer(rng, tuple(sh), float.fromhex(case['sparsities_hex'][n + '/mask:0']),
+                   noise_std=1e-5, slots=1) for n, sh in case['layers']]
+  _run_case(layers, 0.3)
+
+
+def test_resnet50_erk80_full_layer_set(golden):
+  """BASELINE config C2's 54 masked tensors (25.5 M weights) in one batched update."""
+  case = [c for c in golden['cases'] if c['tag'] == 'r50_erk80'][0]
+  rng = np.random.RandomState(14)
+  layers = [_layer(rng, tuple(sh), float.fromhex(case['sparsities_hex'][n + '/mask:0']), slots=1)
+            for n, sh in case['layers']]
+  stats = _run_case(layers, 0.3)
+  assert sum(s[0] for s in stats) == 5100630
+
+
+def test_idempotent_count_and_repeatability():
+  """Size-independent properties at full size: #ones conserved; two identical runs agree."""
+  rng = np.random.RandomState(15)
+  ly = _layer(rng, (3, 3, 512, 512), 0.956534)
+  outs = []
+  for _ in range(2):
+    mv = MaskVariable('big', ly['mask'].shape, DEV)
+    mv.assign(ly['mask'])
+    w, g = _t(ly['w']).view(-1), _t(ly['g']).view(-1)
+    eng = MaskUpdateEngine()
+    eng.run([dict(mask=mv, weights=w, score_grow=g)], np.float32(0.3))
+    outs.append(mv.bits.clone())
+    assert mv.count_ones() == int(ly['mask'].sum())
+  assert torch.equal(outs[0], outs[1])
