@@ -1,0 +1,146 @@
+"""Masked conv / linear fprop, dgrad and dense wgrad vs the float64 CPU oracle.
+
+Tolerance (floating point, north_star: 1e-5 rel on fp32 accumulators): inputs are
+rounded to bf16 ONCE on the host and fed identically to both sides, so the only
+differences are fp32 accumulation order (checked at rtol 2e-5 of the output scale
+on the fp32 outputs) and the single final rounding to bf16 (<= 1 bf16 ulp =
+2^-8 relative, checked on the bf16 outputs).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rigl_oracle as orc
+from rigl_b200 import _cabi
+from rigl_b200.layers import SparseConv2d, SparseLinear
+from rigl_b200 import pruning
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _bf16(a):
+  return torch.from_numpy(np.asarray(a, np.float32)).to(torch.bfloat16)
+
+
+def _check_bf16(got, want, what):
+  got = got.float().cpu().numpy().astype(np.float64)
+  scale = np.abs(want).max() + 1e-30
+  err = np.abs(got - want)
+  tol = np.maximum(np.abs(want) * 2.0 ** -8, scale * 2.0 ** -16) * 1.01 + scale * 2e-5
+  assert (err <= tol).all(), '%s: max err %g (scale %g) at %d positions' % (
+      what, err.max(), scale, int((err > tol).sum()))
+
+
+def _check_f32(got, want, what, rtol=2e-5):
+  got = got.float().cpu().numpy().astype(np.float64)
+  scale = np.abs(want).max() + 1e-30
+  assert np.abs(got - want).max() <= rtol * scale, '%s: max err %g scale %g' % (
+      what, np.abs(got - want).max(), scale)
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, sparsity
+    (2, 8, 8, 16, 32, 3, 1, 0.5),
+    (2, 9, 7, 8, 16, 3, 2, 0.8),
+    (3, 8, 8, 64, 64, 1, 1, 0.0),
+    (2, 14, 14, 64, 128, 1, 2, 0.4),
+    (2, 12, 12, 3, 8, 7, 2, 0.14),      # stem-like: cin=3 (SIMT path)
+    (4, 16, 16, 64, 64, 3, 1, 0.64),
+    (8, 14, 14, 128, 128, 3, 1, 0.82),
+    (4, 28, 28, 128, 128, 3, 2, 0.82),
+    (16, 7, 7, 256, 256, 3, 1, 0.95),
+    (32, 7, 7, 512, 128, 1, 1, 0.7),
+]
+
+
+def _conv_case(case, force_simt):
+  n, h, w, cin, cout, k, stride, sparsity = case
+  rng = np.random.RandomState(hash(case) % (2 ** 31))
+  pruning.reset_default_registry()
+  _cabi.lib().rigl_set_force_simt(1 if force_simt else 0)
+  try:
+    layer = SparseConv2d(cin, cout, k, strides=stride, name='t', device=DEV)
+    w_np = _bf16(rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).float().numpy()
+    m_np = orc.get_mask_random_numpy((k, k, cin, cout), sparsity, rng).astype(np.float32)
+    with torch.no_grad():
+      layer.weight.copy_(torch.from_numpy(w_np))
+    layer.mask.assign(m_np)
+    x_np = _bf16(rng.standard_normal((n, h, w, cin))).float().numpy()
+    x = torch.from_numpy(x_np).permute(0, 3, 1, 2).to(DEV).to(torch.bfloat16) \
+        .contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = layer(x)
+    wm = (w_np * m_np).astype(np.float64)
+    pad = (k - 1) // 2
+    y_want = orc.conv2d_nhwc_fwd(x_np.astype(np.float64), wm, stride, pad)
+    assert tuple(y.shape) == (n, cout, y_want.shape[1], y_want.shape[2])
+    _check_bf16(y.permute(0, 2, 3, 1), y_want, 'fprop %s' % (case,))
+    dy_np = _bf16(rng.standard_normal(y_want.shape)).float().numpy()
+    dy = torch.from_numpy(dy_np).permute(0, 3, 1, 2).to(DEV).to(torch.bfloat16) \
+        .contiguous(memory_format=torch.channels_last)
+    y.backward(dy)
+    dx_want, dw_want = orc.conv2d_nhwc_bwd(x_np.astype(np.float64), wm, dy_np.astype(np.float64), stride, pad)
+    _check_bf16(x.grad.permute(0, 2, 3, 1), dx_want, 'dgrad %s' % (case,))
+    # dense wgrad: every position, including masked-out ones (RigL grow scores)
+    _check_f32(layer.masked_weights.dense_grad.view(k, k, cin, cout), dw_want, 'wgrad %s' % (case,))
+    # dL/dweights = mask * dense
+    _check_f32(layer.weight.grad, dw_want * m_np, 'masked wgrad %s' % (case,))
+    assert (layer.weight.grad.cpu().numpy()[m_np == 0] == 0).all()
+  finally:
+    _cabi.lib().rigl_set_force_simt(0)
+
+
+@pytest.mark.parametrize('case', CONV_CASES[:6])
+def test_conv_simt_path(case):
+  _conv_case(case, force_simt=True)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_default_path(case):
+  _conv_case(case, force_simt=False)
+
+
+LINEAR_CASES = [(1, 3, 5, 0.5), (100, 784, 300, 0.9), (100, 300, 100, 0.81), (100, 100, 10, 0.0),
+                (256, 2048, 1000, 0.85), (37, 64, 64, 0.3)]
+
+
+@pytest.mark.parametrize('case', LINEAR_CASES)
+@pytest.mark.parametrize('force_simt', [True, False])
+def test_linear(case, force_simt):
+  m_rows, n_in, n_out, sparsity = case
+  rng = np.random.RandomState(m_rows + n_in)
+  pruning.reset_default_registry()
+  _cabi.lib().rigl_set_force_simt(1 if force_simt else 0)
+  try:
+    layer = SparseLinear(n_in, n_out, name='fc', device=DEV, out_dtype=torch.float32)
+    w_np = _bf16(rng.standard_normal((n_in, n_out)) / np.sqrt(n_in)).float().numpy()
+    m_np = orc.get_mask_random_numpy((n_in, n_out), sparsity, rng).astype(np.float32)
+    b_np = rng.standard_normal(n_out).astype(np.float32)
+    with torch.no_grad():
+      layer.weight.copy_(torch.from_numpy(w_np))
+      layer.bias.copy_(torch.from_numpy(b_np))
+    layer.mask.assign(m_np)
+    x_np = _bf16(rng.standard_normal((m_rows, n_in))).float().numpy()
+    x = torch.from_numpy(x_np).to(DEV).to(torch.bfloat16).requires_grad_(True)
+    y = layer(x)
+    assert y.dtype == torch.float32
+    y_want = orc.masked_linear_fwd(x_np, w_np, m_np, b_np)
+    _check_f32(y, y_want, 'linear fprop')
+    dy_np = _bf16(rng.standard_normal(y_want.shape)).float().numpy()
+    y.backward(torch.from_numpy(dy_np).to(DEV))
+    dx_want, dw_dense, dw_masked = orc.masked_linear_bwd(x_np, w_np, m_np, dy_np)
+    _check_bf16(x.grad, dx_want, 'linear dgrad')
+    _check_f32(layer.masked_weights.dense_grad.view(n_in, n_out), dw_dense, 'linear dense wgrad')
+    _check_f32(layer.weight.grad, dw_masked, 'linear masked wgrad')
+    _check_f32(layer.bias.grad, dy_np.astype(np.float64).sum(0), 'bias grad')
+  finally:
+    _cabi.lib().rigl_set_force_simt(0)
+
+
+def test_rank_and_channel_errors():
+  pruning.reset_default_registry()
+  layer = SparseConv2d(8, 8, 3, name='e', device=DEV)
+  with pytest.raises(ValueError):
+    layer(torch.zeros(2, 8, 4, device=DEV))
+  with pytest.raises(ValueError):
+    layer(torch.zeros(2, 4, 4, 4, device=DEV))

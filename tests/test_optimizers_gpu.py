@@ -1,0 +1,199 @@
+"""Port of the reference's optimizer tests (rigl/sparse_optimizers_test.py) to the
+PyTorch/CUDA backend: same fixtures (one masked fully-connected layer, constant
+inputs, analytically known gradients), same assertions, plus oracle parity of a
+full RigL update through the public optimizer API."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rigl_oracle as orc
+from rigl_b200 import pruning, sparse_optimizers
+from rigl_b200.layers import SparseLinear
+from rigl_b200.sparse_optimizers_base import GlobalStep
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _setup_set(n_inp, n_out, drop_frac, start_iter=1, end_iter=4, freq_iter=2, cls=None):
+  pruning.reset_default_registry()
+  torch.manual_seed(0)
+  np.random.seed(0)
+  layer = SparseLinear(n_inp, n_out, name='fully_connected', device=DEV, out_dtype=torch.float32)
+  optim = torch.optim.SGD(layer.parameters(), lr=0.1)
+  cls = cls or sparse_optimizers.SparseSETOptimizer
+  sparse_optim = cls(optim, start_iter, end_iter, freq_iter, drop_fraction=drop_frac)
+  layer.mask.assign(np.random.choice([0, 1], size=(n_inp, n_out), p=[1. / 2, 1. / 2]))
+  gs = GlobalStep(0)
+
+  def train_op():
+    x = torch.rand(1, n_inp, device=DEV)
+    loss = layer(x).mean()
+    sparse_optim.minimize(loss, gs)
+
+  return train_op, layer, gs, sparse_optim
+
+
+@pytest.mark.parametrize('n_inp,n_out,drop_frac', [(15, 25, 0.5), (15, 25, 0.2), (3, 5, 0.2)])
+def test_set_mask_non_update_iterations(n_inp, n_out, drop_frac):
+  train_op, layer, _, _ = _setup_set(n_inp, n_out, drop_frac)
+  for i in range(1, 6):
+    before = layer.mask.numpy()
+    train_op()
+    if i not in (1, 3):
+      assert np.array_equal(before, layer.mask.numpy())
+
+
+@pytest.mark.parametrize('n_inp,n_out,drop_frac', [(15, 25, 0.5), (15, 25, 0.7), (30, 10, 0.9)])
+def test_set_update_iterations(n_inp, n_out, drop_frac):
+  train_op, layer, _, _ = _setup_set(n_inp, n_out, drop_frac)
+  for i in range(1, 5):
+    before = layer.mask.numpy()
+    train_op()
+    after = layer.mask.numpy()
+    if i in (1, 3):
+      assert before.sum() == after.sum()
+      assert not np.array_equal(before, after)
+
+
+@pytest.mark.parametrize('start_iter,end_iter,freq_iter', [(3, 7, 2), (1, 5, 3), (0, 4, 1)])
+def test_set_no_drop(start_iter, end_iter, freq_iter):
+  train_op, layer, _, _ = _setup_set(3, 5, 0, start_iter, end_iter, freq_iter)
+  for _ in range(end_iter + 2):
+    before = layer.mask.numpy()
+    train_op()
+    assert np.array_equal(before, layer.mask.numpy())
+
+
+def test_set_new_connection_zero_init():
+  train_op, layer, _, _ = _setup_set(3, 5, 0.5, start_iter=0, end_iter=4, freq_iter=1)
+  for _ in range(5):
+    before = layer.mask.numpy()
+    train_op()
+    after = layer.mask.numpy()
+    w = layer.weight.detach().cpu().numpy()
+    assert np.all(w[np.logical_and(before == 0, after == 1)] == 0)
+
+
+@pytest.mark.parametrize('shape,init_type', list(itertools.product(
+    ((3, 7, 2), (5, 3), (1,)), ('zeros', 'random_normal', 'random_uniform'))))
+def test_shape_and_dtype_of_grow_tensor(shape, init_type):
+  pruning.reset_default_registry()
+  p = torch.nn.Parameter(torch.rand(shape, device=DEV))
+  so = sparse_optimizers.SparseSETOptimizer(torch.optim.SGD([p], lr=0.1), 0, 0, 1, use_stateless=False)
+  for dtype in (torch.float32, torch.float64):
+    w = torch.rand(shape, device=DEV, dtype=dtype) * 5
+    g = so.get_grow_tensor(w, init_type)
+    assert g.shape == w.shape and g.dtype == w.dtype
+
+
+@pytest.mark.parametrize('method', ['ones', 'zero', None, 0])
+def test_value_error_of_grow_tensor(method):
+  p = torch.nn.Parameter(torch.rand(3, 4, device=DEV))
+  so = sparse_optimizers.SparseSETOptimizer(torch.optim.SGD([p], lr=0.1), 0, 0, 1, use_stateless=False)
+  with pytest.raises(ValueError):
+    so.get_grow_tensor(p, method)
+
+
+@pytest.mark.parametrize('n_inp,n_out,drop_frac', [(15, 25, 0.5), (15, 25, 0.7), (30, 10, 0.9)])
+def test_static_mask_never_changes(n_inp, n_out, drop_frac):
+  train_op, layer, _, _ = _setup_set(n_inp, n_out, drop_frac, cls=sparse_optimizers.SparseStaticOptimizer)
+  first = layer.mask.numpy()
+  for _ in range(5):
+    train_op()
+    assert np.array_equal(first, layer.mask.numpy())
+
+
+def _setup_rigl(n_inp, n_out, drop_frac, start_iter=1, end_iter=4, freq_iter=2):
+  pruning.reset_default_registry()
+  layer = SparseLinear(n_inp, n_out, name='fully_connected', device=DEV, out_dtype=torch.float32)
+  optim = torch.optim.SGD(layer.parameters(), lr=1e-3)
+  gs = GlobalStep(0)
+  so = sparse_optimizers.SparseRigLOptimizer(optim, start_iter, end_iter, freq_iter, drop_fraction=drop_frac)
+
+  def train_op():
+    x = torch.ones(1, n_inp, device=DEV)
+    y = layer(x)
+    scale = (torch.arange(y.numel(), device=DEV, dtype=y.dtype).reshape(y.shape) * float(gs.value))
+    loss = (y * scale).sum()
+    so.minimize(loss, gs)
+    return scale
+
+  return train_op, layer, gs, so
+
+
+@pytest.mark.parametrize('n_inp,n_out', [(3, 4), (5, 2), (2, 5)])
+def test_rigl_masked_gradient_calculation(n_inp, n_out):
+  # sparse_optimizers_test.py:330-347: the dense gradient equals the broadcast scale vector.
+  train_op, layer, gs, so = _setup_rigl(n_inp, n_out, 0., start_iter=0, end_iter=3, freq_iter=1)
+  for _ in range(6):
+    scale = train_op()
+    dense = so._weight2masked_grads[layer.weight.name].view(n_inp, n_out)
+    assert torch.equal(dense, scale.expand(n_inp, n_out).float())
+
+
+@pytest.mark.parametrize('sched,expect', [
+    ((3, 7, 2), [1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 1]),
+    ((1, 5, 3), [1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1]),
+    ((0, 4, 1), [0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1])])
+def test_rigl_apply_gradients(sched, expect):
+  train_op, layer, gs, _ = _setup_rigl(3, 5, .5, *sched)
+  for one_if_incremented in expect:
+    before = gs.value
+    train_op()
+    assert gs.value - before == one_if_incremented
+
+
+def test_rigl_update_through_public_api_matches_oracle():
+  """One real RigL update (momentum slots, injected noise stream) vs the oracle."""
+  pruning.reset_default_registry()
+  torch.manual_seed(1)
+  rng = np.random.RandomState(1)
+  layers = [SparseLinear(784, 300, name='layer1', device=DEV), SparseLinear(300, 100, name='layer2', device=DEV),
+            SparseLinear(100, 10, name='layer3', device=DEV, out_dtype=torch.float32)]
+  for l, s in zip(layers, (0.9, 0.81, 0.0)):
+    l.mask.assign(orc.get_mask_random_numpy(tuple(l.weight.shape), s, rng))
+  params = [p for l in layers for p in l.parameters()]
+  optim = torch.optim.SGD(params, lr=0.2, momentum=0.9, nesterov=True)
+  so = sparse_optimizers.SparseRigLOptimizer(optim, 0, 50000, 100, drop_fraction=0.3,
+                                             drop_fraction_anneal='cosine', initial_acc_scale=0.25)
+  gs = GlobalStep(0)
+  x = torch.randn(100, 784, device=DEV)
+  target = torch.randint(0, 10, (100,), device=DEV)
+
+  def loss_fn():
+    h = torch.relu(layers[0](x))
+    h = torch.relu(layers[1](h))
+    return torch.nn.functional.cross_entropy(layers[2](h).float(), target)
+
+  # step 0 is an update iteration (last_update = -freq): no optimizer step, gs frozen
+  so.minimize(loss_fn(), gs)
+  assert gs.value == 0 and so.last_update_was_mask_update
+  # a normal step creates the momentum slots
+  so.minimize(loss_fn(), gs)
+  assert gs.value == 1
+  for _ in range(99):
+    so.minimize(loss_fn(), gs)
+  assert gs.value == 100
+  # snapshot, then the update at gs=100
+  snap = []
+  loss = loss_fn()
+  grads_and_vars = so.compute_gradients(loss)
+  for l in layers:
+    snap.append(dict(mask=l.mask.numpy(), w=l.weight.detach().cpu().numpy().copy(),
+                     g=l.masked_weights.dense_grad.cpu().numpy().reshape(l.weight.shape).copy(),
+                     mom=optim.state[l.weight]['momentum_buffer'].cpu().numpy().copy()))
+  so.apply_gradients(grads_and_vars, gs)
+  assert gs.value == 100 and so.last_update_was_mask_update
+  frac = orc.get_drop_fraction('cosine', 0.3, 100, 0, 50000, True)
+  assert np.float32(so.drop_fraction) == frac
+  for l, s in zip(layers, snap):
+    noise = so._noise_bufs[l.weight.name].cpu().numpy().reshape(s['w'].shape)
+    want = orc.rigl_mask_update(s['mask'], s['w'], s['g'], frac, noise=noise, initial_acc_scale=0.25,
+                                slots=[s['mom']])
+    assert np.array_equal(l.mask.numpy(), want['mask'])
+    assert l.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes()
+    assert optim.state[l.weight]['momentum_buffer'].cpu().numpy().tobytes() == want['slots'][0].tobytes()
+    assert l.mask.count_ones() == int(s['mask'].sum())
