@@ -1,11 +1,776 @@
-// tcgen05 implicit-GEMM path -- placeholder until the kernels land (next commit).
+// Masked conv2d / linear as implicit GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   fprop : y[pix, co]  = sum_{tap, ci} x[pix (+) tap, ci] * Wm[tap][co][ci]
+//   dgrad : dx[pix, ci] = sum_{tap, co} dy[pix (-) tap, co] * Wm[tap][ci][co]
+//   wgrad : dW[tap][ci][co] = sum_{pix} x[pix (+) tap, ci] * dy[pix, co]      (dense, fp32)
+// Wm = mask * W is produced once per step by pack.cu; its per-tile survivor counts
+// gate the weight-tile loads (an all-zero 64x64 weight tile costs no TMA and no MMA).
+//
+// No im2col buffer exists anywhere: an M tile is a BOX of 128 output pixels
+// (bw x bh x bn over width, height, batch) and, for filter tap (kh,kw), the A
+// operand is the same box shifted by the tap offset, fetched by ONE 4-D TMA
+// (cp.async.bulk.tensor.4d) whose out-of-bounds zero fill implements the padding.
+// Stride-2 convs read through four parity sub-grid tensor maps (same trick,
+// element strides doubled), so every conv shape in ResNet/WRN is a plain loop of
+// TMA boxes + tcgen05.mma with fp32 accumulators in TMEM.
+//
+// Kernel organisation (persistent, one CTA per SM, 192 threads):
+//   warp 0    : TMA producer (one elected lane)      smem ring, full/empty mbarriers
+//   warp 1    : TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, M=128
+//   warps 2-5 : epilogue: tcgen05.ld 32x32b -> registers -> bf16/fp32 global stores,
+//               double-buffered accumulators so the epilogue of tile i overlaps the
+//               main loop of tile i+1.
+// fprop/dgrad use K-major operands; wgrad reduces over pixels, so both operands are
+// MN-major views of the NHWC tensors (no transposes are materialised) and the
+// pixel range is split across CTAs (deterministic two-pass split-K).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
 #include "common.cuh"
 #include "conv_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace rigl {
-bool tc_supported(const ConvGeom&, int) { return false; }
-size_t tc_workspace_bytes(const ConvGeom&) { return 0; }
-int tc_fprop(const ConvGeom&, const void*, const void*, void*, float*, const float*, void*, size_t, cudaStream_t) { return RIGL_ERR_UNSUPPORTED; }
-int tc_dgrad(const ConvGeom&, const void*, const void*, void*, void*, size_t, cudaStream_t) { return RIGL_ERR_UNSUPPORTED; }
-int tc_wgrad(const ConvGeom&, const void*, const void*, float*, float, void*, size_t, cudaStream_t) { return RIGL_ERR_UNSUPPORTED; }
+
+using namespace ptx;
+
+constexpr int kMaxTaps = 9;
+constexpr int kBM = 128;            // UMMA M
+constexpr int kBK = 64;             // K block: 64 bf16 = one 128B swizzle row
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct TapInfo {
+  int8_t map_id, dh, dw, pad;
+  int32_t b_tap;                    // tap index into the packed weights
+};
+
+struct IgemmParams {
+  int ntaps;
+  TapInfo taps[kMaxTaps];
+  int kblks;                        // K blocks per tap
+  int GW, GH, NB;                   // pixel grid covered by this launch
+  int bw, bh, bn;                   // pixel box of one M tile (bw*bh*bn == 128)
+  int tiles_w, tiles_h, tiles_n;    // boxes per dimension
+  int n_tiles;                      // tiles along the output-channel dim
+  int N;                            // output channels
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  const float* bias;
+  long long o_off, o_sn, o_sh, o_sw;   // element offsets of pixel (n,h,w) in the output
+  const uint32_t* nnz;              // survivor counts per 64x64 weight tile (or null)
+  int nnz_tap_stride, nnz_n_stride, nnz_k_stride;
+};
+
+struct TMaps4 {
+  CUtensorMap a[4];
+};
+
+__device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_idx, int n_tile, int kb, int bn64) {
+  if (p.nnz == nullptr) return true;
+  const uint32_t* base = p.nnz + (long long)p.taps[tap_idx].b_tap * p.nnz_tap_stride + (long long)kb * p.nnz_k_stride;
+  uint32_t s = 0;
+  for (int j = 0; j < bn64; ++j) {
+    const int nt = n_tile * bn64 + j;
+    if ((long long)nt * 64 < p.N) s += __ldg(base + (long long)nt * p.nnz_n_stride);
+  }
+  return s != 0;
+}
+
+// ----------------------------------------------------------------------------
+// fprop / dgrad kernel: D[128 pixels, BN] += A[128, 64] * B[BN, 64]^T per (tap, k block)
+// ----------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUtensorMap bmap,
+               const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
+  constexpr uint32_t kBBytes = BN * kBK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 0, 0);
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
+    prefetch_tmap(&bmap);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  constexpr int kBN64 = (BN + 63) / 64;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        bool first = true;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const TapInfo tap = p.taps[t];
+          for (int kb = 0; kb < p.kblks; ++kb) {
+            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
+            first = false;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * kStageBytes;
+            const uint32_t b_dst = a_dst + kABytes;
+            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+            tma_load_4d(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                        th * p.bh + tap.dh, tn * p.bn);
+            tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN, tap.b_tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        bool first = true;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int kb = 0; kb < p.kblks; ++kb) {
+            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + stage * kStageBytes;
+            const uint32_t b_src = a_src + kABytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_src + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc(b_src + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, kIdesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(acc));                       // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                            // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;                     // pixel index inside the box
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int pw = tw * p.bw + row % p.bw;
+      const int ph = th * p.bh + (row / p.bw) % p.bh;
+      const int pn = tn * p.bn + row / (p.bw * p.bh);
+      const bool pix_ok = pw < p.GW && ph < p.GH && pn < p.NB;
+      const long long o_pix = p.o_off + pn * p.o_sn + ph * p.o_sh + pw * p.o_sw;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        const int co0 = n_tile * BN + c0;
+        if (pix_ok && co0 < p.N) {
+          if (p.out_bf16) {
+            __nv_bfloat16* dst = p.out_bf16 + o_pix + co0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (co0 + j + 8 <= p.N) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float a = __uint_as_float(r[j + 2 * q]), b = __uint_as_float(r[j + 2 * q + 1]);
+                  if (p.bias) { a += __ldg(p.bias + co0 + j + 2 * q); b += __ldg(p.bias + co0 + j + 2 * q + 1); }
+                  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                  pk[q] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              } else {
+                for (int q = 0; q < 8 && co0 + j + q < p.N; ++q) {
+                  float a = __uint_as_float(r[j + q]);
+                  if (p.bias) a += __ldg(p.bias + co0 + j + q);
+                  dst[j + q] = __float2bfloat16(a);
+                }
+              }
+            }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + o_pix + co0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (co0 + j + 4 <= p.N) {
+                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                if (p.bias) {
+                  v.x += __ldg(p.bias + co0 + j); v.y += __ldg(p.bias + co0 + j + 1);
+                  v.z += __ldg(p.bias + co0 + j + 2); v.w += __ldg(p.bias + co0 + j + 3);
+                }
+                *reinterpret_cast<float4*>(dst + j) = v;
+              } else {
+                for (int q = 0; q < 4 && co0 + j + q < p.N; ++q) {
+                  float a = __uint_as_float(r[j + q]);
+                  if (p.bias) a += __ldg(p.bias + co0 + j + q);
+                  dst[j + q] = a;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// wgrad kernel: D[128 ci, BN co] += X^T[ci, 64 pix] * dY[64 pix, co]  (both MN-major)
+// ----------------------------------------------------------------------------
+struct WgradParams {
+  int ntaps;
+  TapInfo taps[kMaxTaps];
+  int GW, GH, NB;                   // output pixel grid (the reduction domain)
+  int bw, bh, bn;                   // pixel box of one K block (bw*bh*bn == 64)
+  int tiles_w, tiles_h, tiles_n;
+  int pblocks, splits, pblocks_per_split;
+  int ci, co;                       // M and N extents
+  int m_tiles, n_tiles;
+  float* out;                       // [splits][taps][ci][co] partials (or dw itself when splits == 1)
+  long long split_stride;           // elements between split slices
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUtensorMap dymap,
+              const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = kBM * kBK * 2;        // two 64-channel boxes of 64 pixels: 16 KB
+  constexpr uint32_t kBBytes = BN * kBK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kBox = 64 * 64 * 2;             // 8 KB: 64 pixels x 64 channels
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 1, 1);
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&xmaps.a[i]);
+    prefetch_tmap(&dymap);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int out_tiles = p.ntaps * p.m_tiles * p.n_tiles;
+  const int total_units = out_tiles * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u / out_tiles;
+        const int ot = u % out_tiles;
+        const int n_tile = ot % p.n_tiles;
+        const int m_tile = (ot / p.n_tiles) % p.m_tiles;
+        const TapInfo tap = p.taps[ot / (p.n_tiles * p.m_tiles)];
+        const int pb0 = split * p.pblocks_per_split;
+        const int pb1 = min(pb0 + p.pblocks_per_split, p.pblocks);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int tw = pb % p.tiles_w;
+          const int th = (pb / p.tiles_w) % p.tiles_h;
+          const int tn = pb / (p.tiles_w * p.tiles_h);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+#pragma unroll
+          for (int h = 0; h < kBM / 64; ++h)
+            tma_load_4d(a_dst + h * kBox, &xmaps.a[tap.map_id], full_bar(stage), m_tile * kBM + h * 64,
+                        tw * p.bw + tap.dw, th * p.bh + tap.dh, tn * p.bn);
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_4d(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
+                        th * p.bh, tn * p.bn);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u / out_tiles;
+        const int pb0 = split * p.pblocks_per_split;
+        const int pb1 = min(pb0 + p.pblocks_per_split, p.pblocks);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + stage * kStageBytes;
+          const uint32_t b_src = a_src + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // 16 pixels = 16 rows of 128 B further down the box
+            const uint64_t da = make_smem_desc(a_src + k * 16 * 128, kBox, 1024);
+            const uint64_t db = make_smem_desc(b_src + k * 16 * 128, kBox, 1024);
+            umma_bf16(d_tmem, da, db, kIdesc, (pb == pb0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int split = u / out_tiles;
+      const int ot = u % out_tiles;
+      const int n_tile = ot % p.n_tiles;
+      const int m_tile = (ot / p.n_tiles) % p.m_tiles;
+      const int tap_idx = ot / (p.n_tiles * p.m_tiles);
+      const int ci = m_tile * kBM + row;
+      float* dst_row = p.out + (long long)split * p.split_stride +
+                       ((long long)p.taps[tap_idx].b_tap * p.ci + ci) * p.co;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        const int co0 = n_tile * BN + c0;
+        if (ci < p.ci && co0 < p.co) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (co0 + j + 4 <= p.co) {
+              *reinterpret_cast<float4*>(dst_row + co0 + j) =
+                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                              __uint_as_float(r[j + 3]));
+            } else {
+              for (int q = 0; q < 4 && co0 + j + q < p.co; ++q) dst_row[co0 + j + q] = __uint_as_float(r[j + q]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dw = beta * dw + sum_s partial[s]   (fixed summation order => deterministic)
+__global__ void k_splitk_reduce(const float* __restrict__ part, long long split_stride, int splits,
+                                float* __restrict__ dw, long long n, float beta) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    float4 acc = beta != 0.f ? *reinterpret_cast<const float4*>(dw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (long long)s * split_stride + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dw + i) = acc;
+  } else {
+    for (long long j = i; j < n; ++j) {
+      float a = beta != 0.f ? dw[j] : 0.f;
+      for (int s = 0; s < splits; ++s) a += part[(long long)s * split_stride + j];
+      dw[j] = a;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static std::once_flag g_once;
+static int g_init_status = RIGL_OK;
+
+static void init_driver() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    g_init_status = RIGL_ERR_DRIVER;
+    return;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (g_num_sms <= 0) g_num_sms = 148;
+}
+
+static int ensure_driver() {
+  std::call_once(g_once, init_driver);
+  return g_init_status;
+}
+
+// bf16 tensor map over `rank` dims (dim 0 innermost, contiguous), 128B swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
+                        gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return RIGL_ERR_DRIVER;
+  }
+  return RIGL_OK;
+}
+
+// Activation view (C, W_r, H_r, N) of an NHWC tensor sub-sampled by `s` at parity (rh, rw).
+static int make_act_map(CUtensorMap* out, const void* base, int nb, int h, int w, int c, int s, int rh, int rw,
+                        const uint32_t box[4]) {
+  const uint64_t hr = (h - rh + s - 1) / s, wr = (w - rw + s - 1) / s;
+  const uint64_t dims[4] = {(uint64_t)c, wr, hr, (uint64_t)nb};
+  const uint64_t strides[3] = {(uint64_t)s * c * 2, (uint64_t)s * w * c * 2, (uint64_t)h * w * c * 2};
+  const uint8_t* p = static_cast<const uint8_t*>(base) + ((size_t)rh * w + rw) * c * 2;
+  return make_tmap(out, p, 4, dims, strides, box);
+}
+
+// Smallest-waste factorisation bw*bh*bn == total (powers of two) for a GW x GH x NB pixel grid.
+static void choose_box(int gw, int gh, int nb, int total, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int w = 1; w <= total; w *= 2)
+    for (int h = 1; w * h <= total; h *= 2) {
+      const int n = total / (w * h);
+      const long long padded = (long long)((gw + w - 1) / w * w) * ((gh + h - 1) / h * h) * ((nb + n - 1) / n * n);
+      // prefer less padding; then longer contiguous runs (larger w, then larger h)
+      const long long score = padded * 1024 - w * 16 - h;
+      if (best < 0 || score < best) { best = score; *bw = w; *bh = h; *bn = n; }
+    }
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int posmod(int a, int b) { return ((a % b) + b) % b; }
+
+bool tc_supported(const ConvGeom& g, int which) {
+  if (g.cin % 8 || g.cout % 8) return false;
+  if (g.stride != 1 && g.stride != 2) return false;
+  if (g.ksize * g.ksize > kMaxTaps) return false;
+  if (g.pad != (g.ksize - 1) / 2 && !(g.pad == 0 && g.ksize == 1)) return false;
+  (void)which;
+  return true;
+}
+
+static size_t wgrad_ws_elems(const ConvGeom& g, int* splits_out, int* bps_out, int bw, int bh, int bn, int bn_tile) {
+  const int tiles_w = (g.out_w + bw - 1) / bw, tiles_h = (g.out_h + bh - 1) / bh, tiles_n = (g.batch + bn - 1) / bn;
+  const int pblocks = tiles_w * tiles_h * tiles_n;
+  const int out_tiles = g.taps() * ((g.cin + kBM - 1) / kBM) * ((g.cout + bn_tile - 1) / bn_tile);
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int splits = (2 * sms + out_tiles - 1) / out_tiles;
+  if (splits > pblocks) splits = pblocks;
+  if (splits < 1) splits = 1;
+  const int bps = (pblocks + splits - 1) / splits;
+  splits = (pblocks + bps - 1) / bps;
+  if (splits_out) *splits_out = splits;
+  if (bps_out) *bps_out = bps;
+  return (size_t)splits * g.taps() * g.cin * g.cout;
+}
+
+static int wgrad_bn_tile(const ConvGeom& g) { return g.cout >= 128 ? 128 : 64; }
+
+size_t tc_workspace_bytes(const ConvGeom& g) {
+  if (!tc_supported(g, 2)) return 0;
+  int bw, bh, bn;
+  choose_box(g.out_w, g.out_h, g.batch, 64, &bw, &bh, &bn);
+  return wgrad_ws_elems(g, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g)) * sizeof(float) + 256;
+}
+
+template <int BN, int STAGES>
+static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const IgemmParams& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  k_igemm_kmajor<BN, STAGES><<<grid, kThreads, smem, s>>>(amaps, bmap, p);
+  RIGL_LAUNCH_CHECK("k_igemm_kmajor");
+  return RIGL_OK;
+}
+
+static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bmap, IgemmParams& p, int bn_tile,
+                           cudaStream_t s) {
+  p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
+  if (bn_tile == 64) return launch_kmajor<64, 8>(amaps, bmap, p, s);
+  if (bn_tile == 128) return launch_kmajor<128, 6>(amaps, bmap, p, s);
+  return launch_kmajor<256, 4>(amaps, bmap, p, s);
+}
+
+static int pick_bn(int n_out, long long m_tiles) {
+  // Keep at least ~1 wave of CTAs busy; otherwise prefer the widest tile (fewest A re-reads).
+  if (n_out > 128 && m_tiles * ((n_out + 255) / 256) >= 148) return 256;
+  if (n_out > 64) return 128;
+  return 64;
+}
+
+int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, float* y_f32, const float* bias,
+             void* ws, size_t ws_bytes, cudaStream_t s) {
+  (void)ws; (void)ws_bytes;
+  int rc = ensure_driver();
+  if (rc != RIGL_OK) return rc;
+  const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  IgemmParams p = {};
+  choose_box(g.out_w, g.out_h, g.batch, 128, &p.bw, &p.bh, &p.bn);
+  p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
+  p.tiles_w = (p.GW + p.bw - 1) / p.bw; p.tiles_h = (p.GH + p.bh - 1) / p.bh; p.tiles_n = (p.NB + p.bn - 1) / p.bn;
+  p.kblks = (g.cin + kBK - 1) / kBK;
+  p.N = g.cout;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(y); p.out_f32 = y_f32; p.bias = bias;
+  p.o_off = 0; p.o_sw = g.cout; p.o_sh = (long long)g.out_w * g.cout; p.o_sn = (long long)g.out_h * g.out_w * g.cout;
+  p.nnz = reinterpret_cast<const uint32_t*>(pk + L.off_nnz);
+  p.nnz_tap_stride = L.n_tiles * L.k_tiles; p.nnz_n_stride = L.k_tiles; p.nnz_k_stride = 1;
+  TMaps4 amaps;
+  const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  bool made[4] = {false, false, false, false};
+  p.ntaps = 0;
+  for (int kh = 0; kh < g.ksize; ++kh)
+    for (int kw = 0; kw < g.ksize; ++kw) {
+      const int rh = posmod(kh - g.pad, g.stride), rw = posmod(kw - g.pad, g.stride);
+      const int id = rh * g.stride + rw;
+      if (!made[id]) {
+        rc = make_act_map(&amaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.stride, rh, rw, abox);
+        if (rc != RIGL_OK) return rc;
+        made[id] = true;
+      }
+      TapInfo& t = p.taps[p.ntaps++];
+      t.map_id = (int8_t)id; t.dh = (int8_t)floordiv(kh - g.pad, g.stride); t.dw = (int8_t)floordiv(kw - g.pad, g.stride);
+      t.b_tap = kh * g.ksize + kw;
+    }
+  for (int i = 0; i < 4; ++i) if (!made[i]) amaps.a[i] = amaps.a[p.taps[0].map_id];
+  const int bn_tile = pick_bn(g.cout, (long long)p.tiles_w * p.tiles_h * p.tiles_n);
+  CUtensorMap bmap;
+  const uint64_t bdims[3] = {(uint64_t)L.cin_pad, (uint64_t)g.cout, (uint64_t)g.taps()};
+  const uint64_t bstr[2] = {(uint64_t)L.cin_pad * 2, (uint64_t)g.cout * L.cin_pad * 2};
+  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
+  rc = make_tmap(&bmap, pk + L.off_fprop, 3, bdims, bstr, bbox);
+  if (rc != RIGL_OK) return rc;
+  return dispatch_kmajor(g.cout, amaps, bmap, p, bn_tile, s);
+}
+
+int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, void* ws, size_t ws_bytes,
+             cudaStream_t s) {
+  (void)ws; (void)ws_bytes;
+  int rc = ensure_driver();
+  if (rc != RIGL_OK) return rc;
+  const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  const int st = g.stride;
+  // classes of input pixels by parity; each class is one launch over its sub-grid
+  bool need_zero = false;
+  for (int ph = 0; ph < st && !need_zero; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      int n = 0;
+      for (int kh = 0; kh < g.ksize; ++kh)
+        for (int kw = 0; kw < g.ksize; ++kw)
+          if (posmod(ph + g.pad - kh, st) == 0 && posmod(pw + g.pad - kw, st) == 0) ++n;
+      if (n == 0) need_zero = true;
+    }
+  if (need_zero) RIGL_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.in_pixels() * g.cin * 2, s));
+  for (int ph = 0; ph < st; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      IgemmParams p = {};
+      p.GH = (g.in_h - ph + st - 1) / st; p.GW = (g.in_w - pw + st - 1) / st; p.NB = g.batch;
+      if (p.GH <= 0 || p.GW <= 0) continue;
+      p.ntaps = 0;
+      for (int kh = 0; kh < g.ksize; ++kh)
+        for (int kw = 0; kw < g.ksize; ++kw)
+          if (posmod(ph + g.pad - kh, st) == 0 && posmod(pw + g.pad - kw, st) == 0) {
+            TapInfo& t = p.taps[p.ntaps++];
+            t.map_id = 0; t.dh = (int8_t)((ph + g.pad - kh) / st); t.dw = (int8_t)((pw + g.pad - kw) / st);
+            t.b_tap = kh * g.ksize + kw;
+          }
+      if (p.ntaps == 0) continue;
+      choose_box(p.GW, p.GH, p.NB, 128, &p.bw, &p.bh, &p.bn);
+      p.tiles_w = (p.GW + p.bw - 1) / p.bw; p.tiles_h = (p.GH + p.bh - 1) / p.bh; p.tiles_n = (p.NB + p.bn - 1) / p.bn;
+      p.kblks = (g.cout + kBK - 1) / kBK;
+      p.N = g.cin;
+      p.out_bf16 = static_cast<__nv_bfloat16*>(dx);
+      p.o_off = ((long long)ph * g.in_w + pw) * g.cin;
+      p.o_sw = (long long)st * g.cin; p.o_sh = (long long)st * g.in_w * g.cin; p.o_sn = (long long)g.in_h * g.in_w * g.cin;
+      // survivor table indexed [tap][co/64][ci/64]: here N = ci, K = co
+      p.nnz = reinterpret_cast<const uint32_t*>(pk + L.off_nnz);
+      p.nnz_tap_stride = L.n_tiles * L.k_tiles; p.nnz_n_stride = 1; p.nnz_k_stride = L.k_tiles;
+      TMaps4 amaps;
+      const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      rc = make_act_map(&amaps.a[0], dy, g.batch, g.out_h, g.out_w, g.cout, 1, 0, 0, abox);
+      if (rc != RIGL_OK) return rc;
+      for (int i = 1; i < 4; ++i) amaps.a[i] = amaps.a[0];
+      const int bn_tile = pick_bn(g.cin, (long long)p.tiles_w * p.tiles_h * p.tiles_n);
+      CUtensorMap bmap;
+      const uint64_t bdims[3] = {(uint64_t)L.cout_pad, (uint64_t)g.cin, (uint64_t)g.taps()};
+      const uint64_t bstr[2] = {(uint64_t)L.cout_pad * 2, (uint64_t)g.cin * L.cout_pad * 2};
+      const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
+      rc = make_tmap(&bmap, pk + L.off_dgrad, 3, bdims, bstr, bbox);
+      if (rc != RIGL_OK) return rc;
+      rc = dispatch_kmajor(g.cin, amaps, bmap, p, bn_tile, s);
+      if (rc != RIGL_OK) return rc;
+    }
+  return RIGL_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const TMaps4& xmaps, const CUtensorMap& dymap, const WgradParams& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_wgrad<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int total = p.ntaps * p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  k_igemm_wgrad<BN, STAGES><<<grid, kThreads, smem, s>>>(xmaps, dymap, p);
+  RIGL_LAUNCH_CHECK("k_igemm_wgrad");
+  return RIGL_OK;
+}
+
+int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, void* ws, size_t ws_bytes,
+             cudaStream_t s) {
+  int rc = ensure_driver();
+  if (rc != RIGL_OK) return rc;
+  WgradParams p = {};
+  choose_box(g.out_w, g.out_h, g.batch, 64, &p.bw, &p.bh, &p.bn);
+  p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
+  p.tiles_w = (p.GW + p.bw - 1) / p.bw; p.tiles_h = (p.GH + p.bh - 1) / p.bh; p.tiles_n = (p.NB + p.bn - 1) / p.bn;
+  p.pblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int bn_tile = wgrad_bn_tile(g);
+  const size_t elems = wgrad_ws_elems(g, &p.splits, &p.pblocks_per_split, p.bw, p.bh, p.bn, bn_tile);
+  p.ci = g.cin; p.co = g.cout;
+  p.m_tiles = (g.cin + kBM - 1) / kBM; p.n_tiles = (g.cout + bn_tile - 1) / bn_tile;
+  const long long n_w = (long long)g.taps() * g.cin * g.cout;
+  const bool direct = (p.splits == 1 && beta == 0.f);
+  if (!direct) {
+    const size_t need = elems * sizeof(float);
+    float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    if (ws == nullptr || ws_bytes < need + 256) {
+      set_error("rigl_conv2d_wgrad_dense: workspace %zu < required %zu", ws_bytes, need + 256);
+      return RIGL_ERR_WORKSPACE;
+    }
+    p.out = wsf; p.split_stride = n_w;
+  } else {
+    p.out = dw; p.split_stride = 0;
+  }
+  TMaps4 xmaps;
+  const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  bool made[4] = {false, false, false, false};
+  p.ntaps = 0;
+  for (int kh = 0; kh < g.ksize; ++kh)
+    for (int kw = 0; kw < g.ksize; ++kw) {
+      const int rh = posmod(kh - g.pad, g.stride), rw = posmod(kw - g.pad, g.stride);
+      const int id = rh * g.stride + rw;
+      if (!made[id]) {
+        rc = make_act_map(&xmaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.stride, rh, rw, box);
+        if (rc != RIGL_OK) return rc;
+        made[id] = true;
+      }
+      TapInfo& t = p.taps[p.ntaps++];
+      t.map_id = (int8_t)id; t.dh = (int8_t)floordiv(kh - g.pad, g.stride); t.dw = (int8_t)floordiv(kw - g.pad, g.stride);
+      t.b_tap = kh * g.ksize + kw;
+    }
+  for (int i = 0; i < 4; ++i) if (!made[i]) xmaps.a[i] = xmaps.a[p.taps[0].map_id];
+  CUtensorMap dymap;
+  rc = make_act_map(&dymap, dy, g.batch, g.out_h, g.out_w, g.cout, 1, 0, 0, box);
+  if (rc != RIGL_OK) return rc;
+  rc = (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s) : launch_wgrad<64, 8>(xmaps, dymap, p, s);
+  if (rc != RIGL_OK) return rc;
+  if (!direct) {
+    const long long threads = (n_w + 3) / 4;
+    k_splitk_reduce<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p.out, p.split_stride, p.splits, dw, n_w, beta);
+    RIGL_LAUNCH_CHECK("k_splitk_reduce");
+  }
+  return RIGL_OK;
+}
+
 }  // namespace rigl

@@ -34,6 +34,13 @@ def _workspace(device, nbytes):
   return ws
 
 
+class NamedParameter(nn.Parameter):
+  """Parameter that can carry the TF-style variable name ('<scope>/weights:0') and the
+  `initial_value` tensor some grow-init modes read (sparse_optimizers_base.py:374-380)."""
+  name = None
+  initial_value = None
+
+
 class MaskedWeights(object):
   """Handle for `mask * weights`; carries the dense gradient buffer."""
 
@@ -90,7 +97,7 @@ class _MaskedLayer(nn.Module):
     self.scope = scope
     w = torch.empty(shape_hwio, dtype=torch.float32, device=device)
     (kernel_initializer or variance_scaling_)(w)
-    self.weight = nn.Parameter(w)
+    self.weight = NamedParameter(w)
     self.weight.name = scope + '/weights:0'
     self.mask = MaskVariable(scope, shape_hwio, device)
     self.masked_weights = MaskedWeights(scope, w.numel(), device)
@@ -198,7 +205,7 @@ class SparseLinear(_MaskedLayer):
     self._setup(name or 'Dense', (int(in_features), int(units)), device, registry,
                 kernel_initializer)
     if use_bias:
-      self.bias = nn.Parameter(torch.zeros(int(units), dtype=torch.float32, device=device))
+      self.bias = NamedParameter(torch.zeros(int(units), dtype=torch.float32, device=device))
       self.bias.name = self.scope + '/biases:0'
     else:
       self.register_parameter('bias', None)
