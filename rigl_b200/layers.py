@@ -26,6 +26,36 @@ from .masks import MaskVariable
 _WS = {}
 
 
+class Profiler(object):
+  """Optional per-call CUDA-event timing of the hot-path kernels (bench.py's roofline leg)."""
+  enabled = False
+  records = []
+
+  @classmethod
+  def start(cls):
+    cls.enabled, cls.records = True, []
+
+  @classmethod
+  def stop(cls):
+    """-> list of (kind, scope, milliseconds); synchronises."""
+    cls.enabled = False
+    torch.cuda.synchronize()
+    out = [(k, sc, s.elapsed_time(e)) for k, sc, s, e in cls.records]
+    cls.records = []
+    return out
+
+
+def _timed(kind, layer, fn):
+  if not Profiler.enabled:
+    return fn()
+  s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  s.record()
+  r = fn()
+  e.record()
+  Profiler.records.append((kind, layer.scope, s, e))
+  return r
+
+
 def _workspace(device, nbytes):
   ws = _WS.get(device)
   if ws is None or ws.numel() < nbytes:
@@ -64,8 +94,8 @@ class _MaskedConvFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, weight, bias, layer, out_f32):
-    layer.pack()
-    y = layer._fprop(x, bias, out_f32)
+    _timed('pack', layer, layer.pack)
+    y = _timed('fprop', layer, lambda: layer._fprop(x, bias, out_f32))
     ctx.layer = layer
     ctx.save_for_backward(x)
     ctx.has_bias = bias is not None
@@ -76,9 +106,9 @@ class _MaskedConvFn(torch.autograd.Function):
     layer = ctx.layer
     x, = ctx.saved_tensors
     dy16 = layer._as_activation(dy, layer.out_channels)
-    dx = layer._dgrad(dy16, x) if ctx.needs_input_grad[0] else None
+    dx = _timed('dgrad', layer, lambda: layer._dgrad(dy16, x)) if ctx.needs_input_grad[0] else None
     mw = layer.masked_weights
-    layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh)
+    _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
     mw.fresh = True
     gw = None
     if ctx.needs_input_grad[1]:

@@ -1,0 +1,163 @@
+"""Workload definitions for the hot path: the masked-layer graphs of the
+reference's models, built on rigl_b200.layers, plus the train-step harness.
+
+Only what BASELINE.json's configs need -- the shapes, variable names and wiring
+that the masked conv/linear kernels and the RigL update run on:
+  ResNet50   rigl/imagenet_resnet/resnet_model.py:396-731 (v1.5: stride on the 3x3;
+             BN after every conv, zero-init gamma on the last BN of a block)
+  MnistFC    rigl/mnist/mnist_train_eval.py:112-160 (784-300-100-10, all masked)
+BN / ReLU / pooling / loss are NOT on the masked path (the reference never masks
+them) and run on stock PyTorch kernels over channels_last bf16 tensors.
+"""
+import numpy as np
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import pruning
+from . import sparse_utils
+from .layers import SparseConv2d, SparseLinear, variance_scaling_
+from .sparse_optimizers import SparseRigLOptimizer
+from .sparse_optimizers_base import GlobalStep
+
+BATCH_NORM_DECAY = 0.9
+BATCH_NORM_EPSILON = 1e-5
+
+
+class _BNReLU(nn.Module):
+  """batch_norm_relu (resnet_model.py:41-80)."""
+
+  def __init__(self, channels, relu=True, init_zero=False, device='cuda'):
+    super(_BNReLU, self).__init__()
+    self.bn = nn.BatchNorm2d(channels, eps=BATCH_NORM_EPSILON, momentum=1.0 - BATCH_NORM_DECAY,
+                             device=device)
+    if init_zero:
+      nn.init.zeros_(self.bn.weight)
+    self.relu = relu
+
+  def forward(self, x):
+    x = self.bn(x)
+    return F.relu(x, inplace=True) if self.relu else x
+
+
+class _Bottleneck(nn.Module):
+
+  def __init__(self, cin, filters, strides, use_projection, name, device, registry):
+    super(_Bottleneck, self).__init__()
+    mk = lambda ci, co, k, s, n: SparseConv2d(ci, co, k, strides=s, name='resnet_model/' + n,
+                                              device=device, registry=registry)
+    self.proj = None
+    if use_projection:
+      self.proj = mk(cin, 4 * filters, 1, strides, 'bottleneck_projection_%s' % name)
+      self.proj_bn = _BNReLU(4 * filters, relu=False, device=device)
+    self.conv1 = mk(cin, filters, 1, 1, 'bottleneck_1_%s' % name)
+    self.bn1 = _BNReLU(filters, device=device)
+    self.conv2 = mk(filters, filters, 3, strides, 'bottleneck_2_%s' % name)
+    self.bn2 = _BNReLU(filters, device=device)
+    self.conv3 = mk(filters, 4 * filters, 1, 1, 'bottleneck_3_%s' % name)
+    self.bn3 = _BNReLU(4 * filters, relu=False, init_zero=True, device=device)
+
+  def forward(self, x):
+    shortcut = x if self.proj is None else self.proj_bn(self.proj(x))
+    y = self.bn1(self.conv1(x))
+    y = self.bn2(self.conv2(y))
+    y = self.bn3(self.conv3(y))
+    return F.relu(y + shortcut, inplace=True)
+
+
+class ResNet50(nn.Module):
+  """ResNet-50 with every conv and the classifier masked (54 masked tensors,
+  names = the reference variable scopes)."""
+
+  def __init__(self, num_classes=1000, device='cuda', registry=None):
+    super(ResNet50, self).__init__()
+    self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
+    reg = self.registry
+    self.initial_conv = SparseConv2d(3, 64, 7, strides=2, name='resnet_model/initial_conv',
+                                     device=device, registry=reg)
+    self.initial_bn = _BNReLU(64, device=device)
+    blocks = []
+    cin = 64
+    for g, (filters, n_blocks, stride) in enumerate(((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)), 1):
+      blocks.append(_Bottleneck(cin, filters, stride, True, 'block_group_projection_block_group%d' % g,
+                                device, reg))
+      cin = 4 * filters
+      for b in range(1, n_blocks):
+        blocks.append(_Bottleneck(cin, filters, 1, False, 'block_group%d_%d_1' % (g, b), device, reg))
+    self.blocks = nn.ModuleList(blocks)
+    self.final_dense = SparseLinear(
+        2048, num_classes, name='resnet_model/final_dense', device=device, registry=reg,
+        out_dtype=torch.float32,
+        kernel_initializer=lambda w: w.normal_(0., .01))      # resnet_model.py:713
+
+  def forward(self, x):
+    x = self.initial_bn(self.initial_conv(x))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for blk in self.blocks:
+      x = blk(x)
+    x = x.mean(dim=(2, 3))
+    return self.final_dense(x)
+
+
+class MnistFC(nn.Module):
+  """mnist_network_fc with model_pruning=True: three masked dense layers + ReLU."""
+
+  def __init__(self, hidden=(300, 100), device='cuda', registry=None):
+    super(MnistFC, self).__init__()
+    self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
+    dims = (784,) + tuple(hidden) + (10,)
+    self.layers = nn.ModuleList([
+        SparseLinear(dims[i], dims[i + 1], name='layer%d' % (i + 1), device=device,
+                     registry=self.registry,
+                     out_dtype=torch.float32 if i == len(dims) - 2 else torch.bfloat16)
+        for i in range(len(dims) - 1)])
+
+  def forward(self, x):
+    for i, l in enumerate(self.layers):
+      x = l(x)
+      if i + 1 < len(self.layers):
+        x = F.relu(x)
+    return x
+
+
+def init_masks(model, method, sparsity, custom_sparsity_map=None, seed=0, erk_power_scale=1.0):
+  """Runs the reference's mask-init path (get_mask_init_fn) on a model's masks."""
+  np.random.seed(seed)
+  fn = sparse_utils.get_mask_init_fn(model.registry.get_masks(), method, sparsity,
+                                     custom_sparsity_map or {}, erk_power_scale=erk_power_scale)
+  return fn()
+
+
+class TrainHarness(object):
+  """One sparse training step, wired like imagenet_train_eval.py:355-430:
+  Nesterov momentum 0.9, weight decay on the raw weights, label smoothing 0.1,
+  SparseRigLOptimizer(drop 0.3 cosine, every 100 steps), optional data parallelism."""
+
+  def __init__(self, model, lr=0.1, momentum=0.9, weight_decay=1e-4, label_smoothing=0.1,
+               drop_fraction=0.3, drop_fraction_anneal='cosine', begin_step=0, end_step=25000,
+               frequency=100, data_parallel=None, optimizer_cls=SparseRigLOptimizer):
+    self.model = model
+    self.label_smoothing = label_smoothing
+    self.inner = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, nesterov=True,
+                                 weight_decay=weight_decay)
+    self.opt = optimizer_cls(self.inner, begin_step, end_step, frequency, drop_fraction=drop_fraction,
+                             drop_fraction_anneal=drop_fraction_anneal,
+                             use_tpu=data_parallel is not None).bind(model.registry)
+    self.global_step = GlobalStep(0)
+    self.dp = data_parallel
+    if self.dp is not None:
+      self.dp.attach(model)
+
+  def step(self, images, labels):
+    """images: bf16 [N,3,H,W] channels_last; labels: int64 [N].  Returns the loss tensor."""
+    for mw in self.model.registry.get_masked_weights():
+      mw.fresh = False
+    self.inner.zero_grad(set_to_none=False)
+    logits = self.model(images)
+    loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
+    loss.backward()
+    if self.dp is not None:
+      self.dp.reduce_gradients(self.model)
+    self.opt.collect_masked_grads()
+    self.opt.apply_gradients(None, global_step=self.global_step)
+    return loss

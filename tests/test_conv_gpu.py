@@ -24,7 +24,7 @@ def _bf16(a):
 
 
 def _check_bf16(got, want, what):
-  got = got.float().cpu().numpy().astype(np.float64)
+  got = got.detach().float().cpu().numpy().astype(np.float64)
   scale = np.abs(want).max() + 1e-30
   err = np.abs(got - want)
   tol = np.maximum(np.abs(want) * 2.0 ** -8, scale * 2.0 ** -16) * 1.01 + scale * 2e-5
@@ -33,7 +33,7 @@ def _check_bf16(got, want, what):
 
 
 def _check_f32(got, want, what, rtol=2e-5):
-  got = got.float().cpu().numpy().astype(np.float64)
+  got = got.detach().float().cpu().numpy().astype(np.float64)
   scale = np.abs(want).max() + 1e-30
   assert np.abs(got - want).max() <= rtol * scale, '%s: max err %g scale %g' % (
       what, np.abs(got - want).max(), scale)
@@ -85,7 +85,7 @@ def _conv_case(case, force_simt):
     _check_f32(layer.masked_weights.dense_grad.view(k, k, cin, cout), dw_want, 'wgrad %s' % (case,))
     # dL/dweights = mask * dense
     _check_f32(layer.weight.grad, dw_want * m_np, 'masked wgrad %s' % (case,))
-    assert (layer.weight.grad.cpu().numpy()[m_np == 0] == 0).all()
+    assert (layer.weight.grad.detach().cpu().numpy()[m_np == 0] == 0).all()
   finally:
     _cabi.lib().rigl_set_force_simt(0)
 

@@ -1,0 +1,96 @@
+"""ResNet-50 sparse train step on the CUDA hot path (small batch / image so it runs in seconds)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rigl_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _reference_forward(model, x):
+  """Same network with stock torch convs on mask*W (bf16, channels_last)."""
+  def conv(layer, t):
+    w = (layer.weight.detach() * layer.mask.to_dense()).to(torch.bfloat16).permute(3, 2, 0, 1).contiguous()
+    return F.conv2d(t, w, stride=layer.stride, padding=layer.pad)
+  t = model.initial_bn(conv(model.initial_conv, x))
+  t = F.max_pool2d(t, 3, 2, 1)
+  for blk in model.blocks:
+    sc = t if blk.proj is None else blk.proj_bn(conv(blk.proj, t))
+    y = blk.bn1(conv(blk.conv1, t))
+    y = blk.bn2(conv(blk.conv2, y))
+    y = blk.bn3(conv(blk.conv3, y))
+    t = F.relu(y + sc)
+  t = t.mean(dim=(2, 3))
+  fc = model.final_dense
+  return t.float() @ (fc.weight.detach() * fc.mask.to_dense()).to(torch.bfloat16).float() + fc.bias.detach()
+
+
+def test_resnet50_layer_table_and_erk_counts(golden):
+  torch.manual_seed(0)
+  model = workloads.ResNet50(device=DEV)
+  case = [c for c in golden['cases'] if c['tag'] == 'r50_erk80'][0]
+  names = [m.name for m in model.registry.get_masks()]
+  assert names == [n + '/mask:0' for n, _ in case['layers']]
+  assert [list(m.shape) for m in model.registry.get_masks()] == [sh for _, sh in case['layers']]
+  sp = workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=0)
+  for m in model.registry.get_masks():
+    assert float(sp[m.name]).hex() == case['sparsities_hex'][m.name]
+    assert m.count_ones() == case['nnz'][m.name]
+
+
+def test_forward_matches_stock_torch_convs():
+  torch.manual_seed(1)
+  model = workloads.ResNet50(device=DEV)
+  workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=1)
+  for blk in model.blocks:                      # make the residual branch non-trivial
+    torch.nn.init.ones_(blk.bn3.bn.weight)
+  model.eval()                                  # BN in inference mode: deterministic comparison
+  x = torch.randn(4, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  with torch.no_grad():
+    got = model(x)
+    want = _reference_forward(model, x)
+  scale = float(want.abs().max())
+  assert torch.isfinite(got).all()
+  assert float((got - want).abs().max()) <= 5e-2 * scale      # 50+ bf16 roundings deep
+
+
+def test_train_steps_update_semantics_and_conservation():
+  torch.manual_seed(2)
+  model = workloads.ResNet50(device=DEV)
+  workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=2)
+  ones_before = [m.count_ones() for m in model.registry.get_masks()]
+  h = workloads.TrainHarness(model, lr=0.05, frequency=3, end_step=100)
+  x = torch.randn(8, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  y = torch.randint(0, 1000, (8,), device=DEV)
+  incs, losses = [], []
+  for _ in range(8):
+    before = h.global_step.value
+    losses.append(float(h.step(x, y)))
+    incs.append(h.global_step.value - before)
+  assert incs == [0, 1, 1, 1, 0, 1, 1, 1]       # gs 0 and gs 3 are update iterations
+  assert all(np.isfinite(losses))
+  assert [m.count_ones() for m in model.registry.get_masks()] == ones_before
+  # dense gradient is dense; masked gradient is zero off-mask
+  l = model.blocks[3].conv2
+  assert float((l.masked_weights.dense_grad != 0).float().mean()) > 0.9
+  off = l.mask.to_dense() == 0
+  assert float(l.weight.grad[off].abs().max()) == 0.0
+  assert losses[-1] < losses[0] * 1.5
+
+
+def test_mnist_fc_trains():
+  torch.manual_seed(3)
+  model = workloads.MnistFC(device=DEV)
+  workloads.init_masks(model, 'random', 0.9, {'layer2': 0.81, 'layer3': 0.0}, seed=3)
+  assert [m.count_ones() for m in model.registry.get_masks()] == [23520, 5700, 1000]
+  h = workloads.TrainHarness(model, lr=0.2, weight_decay=0.0, label_smoothing=0.0, frequency=100, end_step=50000)
+  x = torch.randn(100, 784, device=DEV)
+  y = (x[:, :10].argmax(1)).long()
+  first = float(h.step(x, y))
+  for _ in range(60):
+    last = float(h.step(x, y))
+  assert last < 0.7 * first
+  assert [m.count_ones() for m in model.registry.get_masks()] == [23520, 5700, 1000]
