@@ -174,6 +174,12 @@ def run_ours(args):
   per_kind = {}
   for kind, _, t in rec:
     per_kind[kind] = per_kind.get(kind, 0.0) + t / prof_steps
+  if args.layer_report:
+    agg = {}
+    for kind, scope, t in rec:
+      agg[(kind, scope)] = agg.get((kind, scope), 0.0) + t / prof_steps
+    with open(args.layer_report, 'w') as f:
+      json.dump([{'kind': k, 'scope': sc, 'ms': v} for (k, sc), v in agg.items()], f, indent=0)
   conv_ms = sum(per_kind.get(k, 0.0) for k in ('fprop', 'dgrad', 'wgrad'))
   n_conv_launch = sum(1 for k, _, _ in rec if k in ('fprop', 'dgrad', 'wgrad')) / prof_steps
   hbm_peak, tf_peak, peak_src = _peaks()
@@ -272,6 +278,7 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--cpu-batch', type=int, default=16)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--layer-report', default=None)
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':
     args.warmup = 3

@@ -149,6 +149,8 @@ typedef struct {
   int32_t batch, in_h, in_w, cin;     /* x  [batch,in_h,in_w,cin]   bf16 NHWC */
   int32_t out_h, out_w, cout;         /* y  [batch,out_h,out_w,cout] bf16 NHWC */
   int32_t ksize, stride, pad;         /* square; pad = (ksize-1)/2 (resnet_model.py:83-108,278-281) */
+  int32_t x_pitch;                    /* elements between consecutive pixels of x (0 => cin); lets a
+                                         zero-padded buffer (e.g. the im2col matrix) be addressed */
 } rigl_conv_desc;
 
 RIGL_API size_t rigl_conv_workspace_bytes(const rigl_conv_desc* d);
@@ -164,6 +166,12 @@ RIGL_API int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, c
  * = sum over pixels x (x) dy.  beta=0 overwrites, beta=1 accumulates into dw. */
 RIGL_API int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, const void* dy,
                                      float* dw, float beta, void* ws, size_t ws_bytes, void* stream);
+/* Patch matrix of a conv whose channel count cannot be addressed by TMA (the 7x7x3 stem,
+ * resnet_model.py:620-633): out[pixel][(kh*k+kw)*cin + ci] = x[n, ho*s+kh-pad, wo*s+kw-pad, ci]
+ * (0 outside), bf16, row pitch out_pitch >= k*k*cin (extra columns zeroed).  The conv then
+ * runs as a masked dense layer over [pixels, k*k*cin] with the SAME HWIO weights and mask. */
+RIGL_API int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* out, int64_t out_pitch,
+                              void* stream);
 /* 1 to route every conv call through the CUDA-core kernels (debug cross-check). */
 RIGL_API int rigl_set_force_simt(int on);
 

@@ -25,7 +25,7 @@ class LayerDesc(C.Structure):
 class ConvDesc(C.Structure):
   _fields_ = [('batch', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('cin', C.c_int32),
               ('out_h', C.c_int32), ('out_w', C.c_int32), ('cout', C.c_int32),
-              ('ksize', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32)]
+              ('ksize', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32), ('x_pitch', C.c_int32)]
 
 
 GROW_ZEROS, GROW_TENSOR, GROW_GRAD_SCALE, GROW_GRAD_SIGN = 0, 1, 2, 3
@@ -53,6 +53,7 @@ SIGNATURES = {
     'rigl_masked_conv2d_fprop': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rigl_masked_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
     'rigl_conv2d_wgrad_dense': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
+    'rigl_im2col_nhwc': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _i64, _vp]),
     'rigl_set_force_simt': (C.c_int, [_i32]),
 }
 

@@ -31,12 +31,23 @@ int geom_from_desc(const rigl_conv_desc* d, ConvGeom* g) {
   g->out_h = d->out_h; g->out_w = d->out_w; g->cout = d->cout;
   g->ksize = d->ksize; g->stride = d->stride; g->pad = d->pad;
   g->cin_pad = round_up8(d->cin); g->cout_pad = round_up8(d->cout);
+  g->x_pitch = d->x_pitch > 0 ? d->x_pitch : d->cin;
+  RIGL_REQUIRE(g->x_pitch >= d->cin, "conv desc: x_pitch %d < cin %d", g->x_pitch, d->cin);
   return RIGL_OK;
 }
 
 }  // namespace rigl
 
 using namespace rigl;
+
+extern "C" int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* out, int64_t out_pitch,
+                                void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && out && out_pitch >= (int64_t)g.taps() * g.cin, "rigl_im2col_nhwc: bad arguments");
+  return simt_im2col(g, x, out, out_pitch, (cudaStream_t)stream);
+}
 
 extern "C" int rigl_set_force_simt(int on) {
   g_force_simt = on ? 1 : 0;

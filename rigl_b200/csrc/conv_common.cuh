@@ -12,6 +12,7 @@ struct ConvGeom {
   int out_h, out_w, cout;
   int ksize, stride, pad;
   int cin_pad, cout_pad;     // rounded up to multiples of 8 (16-byte bf16 rows)
+  int x_pitch;               // elements between pixels of x (>= cin)
   __host__ __device__ int64_t out_pixels() const { return (int64_t)batch * out_h * out_w; }
   __host__ __device__ int64_t in_pixels() const { return (int64_t)batch * in_h * in_w; }
   __host__ __device__ int taps() const { return ksize * ksize; }
@@ -48,6 +49,7 @@ int simt_fprop(const ConvGeom& g, const void* x, const void* w_dgrad, void* y, f
                const float* bias, cudaStream_t s);
 int simt_dgrad(const ConvGeom& g, const void* dy, const void* w_fprop, void* dx, cudaStream_t s);
 int simt_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, cudaStream_t s);
+int simt_im2col(const ConvGeom& g, const void* x, void* out, int64_t out_pitch, cudaStream_t s);
 
 // tcgen05 path (igemm_tc.cu)
 bool tc_supported(const ConvGeom& g, int which /*0 fprop, 1 dgrad, 2 wgrad*/);

@@ -13,12 +13,12 @@
 namespace rigl {
 
 // y[p, co] = sum_{tap, ci} x[pix(p, tap), ci] * wd[tap][ci][co]      (wd = w_dgrad layout)
-// grid: (ceil(cout/64), ceil(pixels/4)); block (64, 4)
+// grid: (ceil(pixels/4), ceil(cout/64)); block (64, 4)
 __global__ void k_simt_fprop(ConvGeom g, const __nv_bfloat16* __restrict__ x,
                              const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ y,
                              float* __restrict__ y_f32, const float* __restrict__ bias) {
-  const int co = blockIdx.x * 64 + threadIdx.x;
-  const int64_t p = (int64_t)blockIdx.y * 4 + threadIdx.y;
+  const int co = blockIdx.y * 64 + threadIdx.x;
+  const int64_t p = (int64_t)blockIdx.x * 4 + threadIdx.y;
   if (p >= g.out_pixels() || co >= g.cout) return;
   const int wo = (int)(p % g.out_w);
   const int ho = (int)((p / g.out_w) % g.out_h);
@@ -30,7 +30,7 @@ __global__ void k_simt_fprop(ConvGeom g, const __nv_bfloat16* __restrict__ x,
     for (int kw = 0; kw < g.ksize; ++kw) {
       const int wi = wo * g.stride + kw - g.pad;
       if (wi < 0 || wi >= g.in_w) continue;
-      const __nv_bfloat16* xr = x + (((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.cin;
+      const __nv_bfloat16* xr = x + (((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch;
       const __nv_bfloat16* wr = wd + (int64_t)(kh * g.ksize + kw) * g.cin * g.cout_pad + co;
       for (int ci = 0; ci < g.cin; ++ci)
         acc = fmaf(__bfloat162float(xr[ci]), __bfloat162float(wr[(int64_t)ci * g.cout_pad]), acc);
@@ -41,11 +41,11 @@ __global__ void k_simt_fprop(ConvGeom g, const __nv_bfloat16* __restrict__ x,
 }
 
 // dx[q, ci] = sum_{tap, co} dy[pix_out(q, tap), co] * wf[tap][co][ci]   (wf = w_fprop layout)
-// grid: (ceil(cin/64), ceil(in_pixels/4)); block (64, 4)
+// grid: (ceil(in_pixels/4), ceil(cin/64)); block (64, 4)
 __global__ void k_simt_dgrad(ConvGeom g, const __nv_bfloat16* __restrict__ dy,
                              const __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ dx) {
-  const int ci = blockIdx.x * 64 + threadIdx.x;
-  const int64_t q = (int64_t)blockIdx.y * 4 + threadIdx.y;
+  const int ci = blockIdx.y * 64 + threadIdx.x;
+  const int64_t q = (int64_t)blockIdx.x * 4 + threadIdx.y;
   if (q >= g.in_pixels() || ci >= g.cin) return;
   const int wi = (int)(q % g.in_w);
   const int hi = (int)((q / g.in_w) % g.in_h);
@@ -67,7 +67,7 @@ __global__ void k_simt_dgrad(ConvGeom g, const __nv_bfloat16* __restrict__ dy,
         acc = fmaf(__bfloat162float(dr[co]), __bfloat162float(wr[(int64_t)co * g.cin_pad]), acc);
     }
   }
-  dx[q * g.cin + ci] = __float2bfloat16(acc);
+  dx[q * g.x_pitch + ci] = __float2bfloat16(acc);
 }
 
 // dw[tap][ci][co] += sum_{p in chunk} x[pix(p,tap), ci] * dy[p, co]
@@ -90,15 +90,47 @@ __global__ void k_simt_wgrad(ConvGeom g, const __nv_bfloat16* __restrict__ x,
     const int n = (int)(p / ((int64_t)g.out_w * g.out_h));
     const int hi = ho * g.stride + kh - g.pad, wi = wo * g.stride + kw - g.pad;
     if (hi < 0 || hi >= g.in_h || wi < 0 || wi >= g.in_w) continue;
-    acc = fmaf(__bfloat162float(x[(((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.cin + ci]),
+    acc = fmaf(__bfloat162float(x[(((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch + ci]),
                __bfloat162float(dy[p * g.cout + co]), acc);
   }
   atomicAdd(dw + o, acc);
 }
 
+// out[p][(kh*k+kw)*cin + ci] = x[pix(p, kh, kw), ci]; one thread per (pixel, kh) copies k*cin
+// contiguous input elements; the kh == 0 thread also zeroes the pad columns.
+__global__ void k_im2col(ConvGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                         int64_t out_pitch) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = t / g.ksize;
+  const int kh = (int)(t % g.ksize);
+  if (p >= g.out_pixels()) return;
+  const int wo = (int)(p % g.out_w);
+  const int ho = (int)((p / g.out_w) % g.out_h);
+  const int n = (int)(p / ((int64_t)g.out_w * g.out_h));
+  const int hi = ho * g.stride + kh - g.pad;
+  __nv_bfloat16* dst = out + p * out_pitch + (int64_t)kh * g.ksize * g.cin;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int kw = 0; kw < g.ksize; ++kw) {
+    const int wi = wo * g.stride + kw - g.pad;
+    const bool ok = hi >= 0 && hi < g.in_h && wi >= 0 && wi < g.in_w;
+    const __nv_bfloat16* src = x + (((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch;
+    for (int ci = 0; ci < g.cin; ++ci) dst[kw * g.cin + ci] = ok ? src[ci] : zero;
+  }
+  if (kh == 0)
+    for (int64_t c = (int64_t)g.taps() * g.cin; c < out_pitch; ++c) out[p * out_pitch + c] = zero;
+}
+
+int simt_im2col(const ConvGeom& g, const void* x, void* out, int64_t out_pitch, cudaStream_t s) {
+  const int64_t threads = g.out_pixels() * g.ksize;
+  k_im2col<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)out,
+                                                             out_pitch);
+  RIGL_LAUNCH_CHECK("k_im2col");
+  return RIGL_OK;
+}
+
 int simt_fprop(const ConvGeom& g, const void* x, const void* w_dgrad, void* y, float* y_f32,
                const float* bias, cudaStream_t s) {
-  dim3 grid((g.cout + 63) / 64, (unsigned)((g.out_pixels() + 3) / 4)), block(64, 4);
+  dim3 grid((unsigned)((g.out_pixels() + 3) / 4), (g.cout + 63) / 64), block(64, 4);
   k_simt_fprop<<<grid, block, 0, s>>>(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_dgrad,
                                       (__nv_bfloat16*)y, y_f32, bias);
   RIGL_LAUNCH_CHECK("k_simt_fprop");
@@ -106,7 +138,7 @@ int simt_fprop(const ConvGeom& g, const void* x, const void* w_dgrad, void* y, f
 }
 
 int simt_dgrad(const ConvGeom& g, const void* dy, const void* w_fprop, void* dx, cudaStream_t s) {
-  dim3 grid((g.cin + 63) / 64, (unsigned)((g.in_pixels() + 3) / 4)), block(64, 4);
+  dim3 grid((unsigned)((g.in_pixels() + 3) / 4), (g.cin + 63) / 64), block(64, 4);
   k_simt_dgrad<<<grid, block, 0, s>>>(g, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w_fprop,
                                       (__nv_bfloat16*)dx);
   RIGL_LAUNCH_CHECK("k_simt_dgrad");

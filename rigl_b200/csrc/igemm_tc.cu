@@ -40,7 +40,6 @@ constexpr int kMaxTaps = 9;
 constexpr int kBM = 128;            // UMMA M
 constexpr int kBK = 64;             // K block: 64 bf16 = one 128B swizzle row
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
 
 struct TapInfo {
   int8_t map_id, dh, dw, pad;
@@ -481,6 +480,13 @@ static void init_driver() {
 }
 
 static int ensure_driver() {
+  // The driver entry point needs a CUDA context current on THIS thread (autograd runs
+  // backward on worker threads that may not have touched the runtime yet).
+  static thread_local bool ctx_ready = false;
+  if (!ctx_ready) {
+    cudaFree(0);
+    ctx_ready = true;
+  }
   std::call_once(g_once, init_driver);
   return g_init_status;
 }
@@ -507,12 +513,12 @@ static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 
 // Activation view (C, W_r, H_r, N) of an NHWC tensor sub-sampled by `s` at parity (rh, rw).
-static int make_act_map(CUtensorMap* out, const void* base, int nb, int h, int w, int c, int s, int rh, int rw,
-                        const uint32_t box[4]) {
+static int make_act_map(CUtensorMap* out, const void* base, int nb, int h, int w, int c, int pitch, int s, int rh,
+                        int rw, const uint32_t box[4]) {
   const uint64_t hr = (h - rh + s - 1) / s, wr = (w - rw + s - 1) / s;
   const uint64_t dims[4] = {(uint64_t)c, wr, hr, (uint64_t)nb};
-  const uint64_t strides[3] = {(uint64_t)s * c * 2, (uint64_t)s * w * c * 2, (uint64_t)h * w * c * 2};
-  const uint8_t* p = static_cast<const uint8_t*>(base) + ((size_t)rh * w + rw) * c * 2;
+  const uint64_t strides[3] = {(uint64_t)s * pitch * 2, (uint64_t)s * w * pitch * 2, (uint64_t)h * w * pitch * 2};
+  const uint8_t* p = static_cast<const uint8_t*>(base) + ((size_t)rh * w + rw) * pitch * 2;
   return make_tmap(out, p, 4, dims, strides, box);
 }
 
@@ -533,7 +539,8 @@ static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b -
 static inline int posmod(int a, int b) { return ((a % b) + b) % b; }
 
 bool tc_supported(const ConvGeom& g, int which) {
-  if (g.cin % 8 || g.cout % 8) return false;
+  if (g.x_pitch % 8 || g.cout % 8) return false;     // 16-byte row pitches for TMA
+  if (which == 1 && g.cin % 8) return false;         // dgrad stores 8 channels at a time
   if (g.stride != 1 && g.stride != 2) return false;
   if (g.ksize * g.ksize > kMaxTaps) return false;
   if (g.pad != (g.ksize - 1) / 2 && !(g.pad == 0 && g.ksize == 1)) return false;
@@ -621,7 +628,7 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
       const int rh = posmod(kh - g.pad, g.stride), rw = posmod(kw - g.pad, g.stride);
       const int id = rh * g.stride + rw;
       if (!made[id]) {
-        rc = make_act_map(&amaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.stride, rh, rw, abox);
+        rc = make_act_map(&amaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.x_pitch, g.stride, rh, rw, abox);
         if (rc != RIGL_OK) return rc;
         made[id] = true;
       }
@@ -658,7 +665,7 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
           if (posmod(ph + g.pad - kh, st) == 0 && posmod(pw + g.pad - kw, st) == 0) ++n;
       if (n == 0) need_zero = true;
     }
-  if (need_zero) RIGL_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.in_pixels() * g.cin * 2, s));
+  if (need_zero) RIGL_CUDA(cudaMemsetAsync(dx, 0, (size_t)g.in_pixels() * g.x_pitch * 2, s));
   for (int ph = 0; ph < st; ++ph)
     for (int pw = 0; pw < st; ++pw) {
       IgemmParams p = {};
@@ -678,14 +685,15 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
       p.kblks = (g.cout + kBK - 1) / kBK;
       p.N = g.cin;
       p.out_bf16 = static_cast<__nv_bfloat16*>(dx);
-      p.o_off = ((long long)ph * g.in_w + pw) * g.cin;
-      p.o_sw = (long long)st * g.cin; p.o_sh = (long long)st * g.in_w * g.cin; p.o_sn = (long long)g.in_h * g.in_w * g.cin;
+      p.o_off = ((long long)ph * g.in_w + pw) * g.x_pitch;
+      p.o_sw = (long long)st * g.x_pitch; p.o_sh = (long long)st * g.in_w * g.x_pitch;
+      p.o_sn = (long long)g.in_h * g.in_w * g.x_pitch;
       // survivor table indexed [tap][co/64][ci/64]: here N = ci, K = co
       p.nnz = reinterpret_cast<const uint32_t*>(pk + L.off_nnz);
       p.nnz_tap_stride = L.n_tiles * L.k_tiles; p.nnz_n_stride = 1; p.nnz_k_stride = L.k_tiles;
       TMaps4 amaps;
       const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-      rc = make_act_map(&amaps.a[0], dy, g.batch, g.out_h, g.out_w, g.cout, 1, 0, 0, abox);
+      rc = make_act_map(&amaps.a[0], dy, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, abox);
       if (rc != RIGL_OK) return rc;
       for (int i = 1; i < 4; ++i) amaps.a[i] = amaps.a[0];
       const int bn_tile = pick_bn(g.cin, (long long)p.tiles_w * p.tiles_h * p.tiles_n);
@@ -751,7 +759,7 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
       const int rh = posmod(kh - g.pad, g.stride), rw = posmod(kw - g.pad, g.stride);
       const int id = rh * g.stride + rw;
       if (!made[id]) {
-        rc = make_act_map(&xmaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.stride, rh, rw, box);
+        rc = make_act_map(&xmaps.a[id], x, g.batch, g.in_h, g.in_w, g.cin, g.x_pitch, g.stride, rh, rw, box);
         if (rc != RIGL_OK) return rc;
         made[id] = true;
       }
@@ -761,7 +769,7 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
     }
   for (int i = 0; i < 4; ++i) if (!made[i]) xmaps.a[i] = xmaps.a[p.taps[0].map_id];
   CUtensorMap dymap;
-  rc = make_act_map(&dymap, dy, g.batch, g.out_h, g.out_w, g.cout, 1, 0, 0, box);
+  rc = make_act_map(&dymap, dy, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, box);
   if (rc != RIGL_OK) return rc;
   rc = (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s) : launch_wgrad<64, 8>(xmaps, dymap, p, s);
   if (rc != RIGL_OK) return rc;

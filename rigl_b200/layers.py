@@ -156,7 +156,12 @@ class _MaskedLayer(nn.Module):
 
 
 class SparseConv2d(_MaskedLayer):
-  """Masked 2-D convolution, square kernel/stride, no bias (resnet_model.py:296)."""
+  """Masked 2-D convolution, square kernel/stride, no bias (resnet_model.py:296).
+
+  Layers whose input-channel count is not a multiple of 8 (the 7x7x3 stem) run in
+  "patch-matrix" mode: `rigl_im2col_nhwc` builds the [pixels, k*k*Cin] matrix once per
+  forward and the conv becomes a masked dense layer over it with the SAME HWIO weights
+  and mask (HWIO flattened over (kh,kw,ci) is exactly the [in,out] matrix)."""
 
   def __init__(self, in_channels, units, kernel_size, strides=1, padding='SAME', name=None,
                kernel_initializer=None, device='cuda', registry=None):
@@ -171,6 +176,20 @@ class SparseConv2d(_MaskedLayer):
     self.pad = (k - 1) // 2 if padding == 'SAME' else 0
     self._setup(name or 'Conv', (k, k, int(in_channels), int(units)), device, registry,
                 kernel_initializer)
+    self.patch_mode = (int(in_channels) % 8 != 0) and k > 1
+    if self.patch_mode:
+      self._kdim = k * k * int(in_channels)
+      self._kpitch = (self._kdim + 7) // 8 * 8
+      nbytes = int(_cabi.lib().rigl_packed_weights_bytes(1, self._kdim, self._cout))
+      self.packed_patch = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+  def pack(self):
+    if self.patch_mode:
+      _cabi.check(_cabi.lib().rigl_pack_masked_weights(
+          self.weight.data_ptr(), self.mask.bits.data_ptr(), 1, self._kdim, self._cout,
+          self.packed_patch.data_ptr(), _cabi.stream_ptr()), 'rigl_pack_masked_weights')
+    else:
+      super(SparseConv2d, self).pack()
 
   def _desc(self, n, h, w):
     d = _cabi.ConvDesc()
@@ -178,6 +197,14 @@ class SparseConv2d(_MaskedLayer):
     d.out_h = (h + 2 * self.pad - self.ksize) // self.stride + 1
     d.out_w = (w + 2 * self.pad - self.ksize) // self.stride + 1
     d.cout, d.ksize, d.stride, d.pad = self._cout, self.ksize, self.stride, self.pad
+    d.x_pitch = 0
+    return d
+
+  def _patch_desc(self, rows):
+    d = _cabi.ConvDesc()
+    d.batch, d.in_h, d.in_w, d.cin = rows, 1, 1, self._kdim
+    d.out_h, d.out_w, d.cout, d.ksize, d.stride, d.pad = 1, 1, self._cout, 1, 1, 0
+    d.x_pitch = self._kpitch
     return d
 
   @staticmethod
@@ -186,20 +213,35 @@ class SparseConv2d(_MaskedLayer):
       t = t.to(torch.bfloat16)
     return t.contiguous(memory_format=torch.channels_last)
 
+  def _patches(self, x):
+    n, c, h, w = x.shape
+    d = self._desc(n, h, w)
+    rows = n * d.out_h * d.out_w
+    a = torch.empty((rows, self._kpitch), dtype=torch.bfloat16, device=x.device)
+    _cabi.check(_cabi.lib().rigl_im2col_nhwc(d, x.data_ptr(), a.data_ptr(), self._kpitch,
+                                             _cabi.stream_ptr()), 'rigl_im2col_nhwc')
+    return a
+
   def _fprop(self, x, bias, out_f32):
     n, c, h, w = x.shape
     d = self._desc(n, h, w)
     y = torch.empty((n, self._cout, d.out_h, d.out_w), dtype=torch.bfloat16, device=x.device,
                     memory_format=torch.channels_last)
+    packed, src = self.packed, x
+    if self.patch_mode:
+      self._patch_cache = src = self._patches(x)
+      d, packed = self._patch_desc(src.shape[0]), self.packed_patch
     ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
     _cabi.check(_cabi.lib().rigl_masked_conv2d_fprop(
-        d, x.data_ptr(), self.packed.data_ptr(), y.data_ptr(), None, None, ws.data_ptr(),
+        d, src.data_ptr(), packed.data_ptr(), y.data_ptr(), None, None, ws.data_ptr(),
         ws.numel(), _cabi.stream_ptr()), 'rigl_masked_conv2d_fprop')
     return y
 
   def _dgrad(self, dy, x):
     n, c, h, w = x.shape
     d = self._desc(n, h, w)
+    if self.patch_mode:                 # rare (image gradients): CUDA-core kernels on the conv form
+      super(SparseConv2d, self).pack()
     dx = torch.empty_like(x, memory_format=torch.channels_last)
     ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
     _cabi.check(_cabi.lib().rigl_masked_conv2d_dgrad(
@@ -209,10 +251,14 @@ class SparseConv2d(_MaskedLayer):
 
   def _wgrad(self, x, dy, out, accumulate):
     n, c, h, w = x.shape
-    d = self._desc(n, h, w)
+    d, src = self._desc(n, h, w), x
+    if self.patch_mode:
+      src = self._patch_cache if getattr(self, '_patch_cache', None) is not None else self._patches(x)
+      self._patch_cache = None
+      d = self._patch_desc(src.shape[0])
     ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
     _cabi.check(_cabi.lib().rigl_conv2d_wgrad_dense(
-        d, x.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
+        d, src.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
         ws.numel(), _cabi.stream_ptr()), 'rigl_conv2d_wgrad_dense')
 
   def forward(self, x):
@@ -244,6 +290,7 @@ class SparseLinear(_MaskedLayer):
     d = _cabi.ConvDesc()
     d.batch, d.in_h, d.in_w, d.cin = m, 1, 1, self._cin
     d.out_h, d.out_w, d.cout, d.ksize, d.stride, d.pad = 1, 1, self._cout, 1, 1, 0
+    d.x_pitch = 0
     return d
 
   @staticmethod

@@ -142,6 +142,16 @@ class SparseSETOptimizerBase(object):
 
   def zero_grad(self, set_to_none=False):
     self._optimizer.zero_grad(set_to_none=set_to_none)
+    self._mark_dense_grads_stale()
+
+  def _mark_dense_grads_stale(self):
+    """The next backward overwrites (rather than accumulates into) the dense-grad buffers."""
+    try:
+      handles = self.get_masked_weights()
+    except NotImplementedError:
+      return
+    for mw in handles:
+      mw.fresh = False
 
   def get_slot_names(self):
     names = []
@@ -176,6 +186,7 @@ class SparseSETOptimizerBase(object):
     for p in self._all_params():
       if p.grad is not None:
         p.grad = None if kwargs.get('set_to_none', False) else p.grad.zero_()
+    self._mark_dense_grads_stale()
     loss.backward()
     return [(p.grad, p) for p in self._all_params()]
 
@@ -328,7 +339,7 @@ class SparseSETOptimizerBase(object):
     if not isinstance(method, str):
       raise ValueError('Grow-Init: %s is not a string' % method)
     w = weights.data if isinstance(weights, torch.nn.Parameter) else weights
-    name = getattr(weights, 'name', 'weights')
+    name = getattr(weights, 'name', None) or 'weights'
     if method == 'zeros':
       return torch.zeros_like(w)
     if method.startswith('initial_dist'):

@@ -36,6 +36,7 @@ SMALL = [
     (4, 56, 56, 64, 64, 3, 1, 0.64),
     (4, 56, 56, 64, 256, 1, 1, 0.0),
     (4, 56, 56, 256, 64, 1, 1, 0.0),
+    (2, 32, 32, 3, 64, 7, 2, 0.14),
 ]
 BIG = [
     (32, 56, 56, 64, 64, 3, 1, 0.64),
@@ -49,6 +50,7 @@ BIG = [
     (32, 7, 7, 512, 512, 3, 1, 0.957),
     (32, 7, 7, 2048, 512, 1, 1, 0.757),
     (32, 14, 14, 1024, 2048, 1, 2, 0.854),
+    (16, 224, 224, 3, 64, 7, 2, 0.14),
 ]
 
 
