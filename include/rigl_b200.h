@@ -172,6 +172,31 @@ RIGL_API int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, con
  * runs as a masked dense layer over [pixels, k*k*cin] with the SAME HWIO weights and mask. */
 RIGL_API int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* out, int64_t out_pitch,
                               void* stream);
+/* ------------------------------------------------------------------------
+ * Fused batch-norm (+ReLU, +residual) over NHWC bf16 activations viewed as [rows, channels]
+ * Replaces batch_norm_relu (rigl/imagenet_resnet/resnet_model.py:41-80) and the
+ * relu(inputs + shortcut) block tail (:501).  channels % 8 == 0.  SURVEY 8(f) row 1.
+ * ---------------------------------------------------------------------- */
+RIGL_API size_t rigl_bn_workspace_bytes(int64_t rows, int channels);
+/* Training forward: batch statistics of y, running-stat update (momentum = 1 - decay, may be
+ * NULL), out = [relu](gamma*(y-mean)*rstd + beta (+ residual)).  save_* [channels] fp32 are kept
+ * for the backward pass (scale = gamma*rstd, shift = beta - mean*scale). */
+RIGL_API int rigl_bn_forward_train(const void* y, const void* residual, const float* gamma,
+                                   const float* beta, int64_t rows, int channels, float eps,
+                                   float momentum, int relu, float* running_mean, float* running_var,
+                                   float* save_mean, float* save_rstd, float* save_scale,
+                                   float* save_shift, void* out, void* ws, size_t ws_bytes, void* stream);
+/* Inference / given statistics: out = [relu](y*scale + shift (+ residual)). */
+RIGL_API int rigl_bn_apply(const void* y, const void* residual, const float* scale, const float* shift,
+                           int64_t rows, int channels, int relu, void* out, void* stream);
+/* Backward.  da = gradient of the output; y = the saved BN input; act = the saved output
+ * (required only in the residual form).  dresidual != NULL selects the residual form and
+ * receives the gradient of the shortcut.  Writes dy, dgamma, dbeta. */
+RIGL_API int rigl_bn_backward(const void* da, const void* y, const void* act, const float* save_mean,
+                              const float* save_rstd, const float* save_scale, const float* save_shift,
+                              int64_t rows, int channels, int relu, void* dy, void* dresidual,
+                              float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
 /* 1 to route every conv call through the CUDA-core kernels (debug cross-check). */
 RIGL_API int rigl_set_force_simt(int on);
 

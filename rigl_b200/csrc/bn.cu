@@ -1,0 +1,345 @@
+// Fused batch-norm (+ReLU, +residual add) for NHWC bf16 activations -- HBM-bound
+// streaming kernels around the masked convs.
+//
+// Replaces batch_norm_relu (rigl/imagenet_resnet/resnet_model.py:41-80:
+// tf.layers.batch_normalization(fused=True, momentum=0.9, epsilon=1e-5) + relu) and the
+// `relu(inputs + shortcut)` tail of the bottleneck block (:501).
+//
+//   forward : stats  : one read of y           -> per-channel mean / rstd (fp32 partials, fp64 combine)
+//             apply  : read y (+residual)      -> a = relu(y*scale + shift (+ r)), bf16
+//   backward: reduce : read da, y (, a)        -> dbeta = sum g, dgamma = sum g*xhat  (g = da * relu')
+//                      (residual form also writes g, which IS the gradient of the shortcut)
+//             apply  : read g|da, y            -> dy = scale * (g - dbeta/M - xhat*dgamma/M)
+// Every kernel moves 16-byte vectors (8 channels) per thread with the channel dimension
+// innermost, so global traffic is fully coalesced; reductions go registers -> smem ->
+// per-block partials -> a tiny finalize kernel (fixed order: deterministic).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rigl {
+
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// Column sums of up to two row-wise quantities over a [rows, C] bf16 matrix.
+// MODE 0: (y, y^2)                                   -> forward statistics
+// MODE 1: (g, g*xhat), g = da * [fma(y,scale,shift) > 0 if relu]      (plain BN / BN+ReLU)
+// MODE 2: (g, g*xhat), g = da * [act > 0], g written to gout          (residual form)
+// partial[block][2][C] fp32.
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da,
+            const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ gout,
+            const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+            const float* __restrict__ shift, int relu, long long rows, int C, long long rows_per_block,
+            float* __restrict__ partial) {
+  extern __shared__ float red[];               // [rpi][V][16]
+  const int V = C >> 3;                         // 16-byte vectors per row
+  const int vl = V < kBnThreads ? V : kBnThreads;
+  const int rpi = kBnThreads / vl;              // rows handled per block iteration
+  const int r_in = threadIdx.x / vl, v0 = threadIdx.x % vl;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const long long row1 = min(row0 + rows_per_block, rows);
+  for (int v = v0; v < V; v += vl) {            // (V > 256 only for C > 2048)
+    float s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+    float mu[8], rs[8], sc[8], sh[8];
+    if (MODE != 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        mu[i] = mean[8 * v + i]; rs[i] = rstd[8 * v + i];
+        sc[i] = scale[8 * v + i]; sh[i] = shift[8 * v + i];
+      }
+    }
+    if (r_in < rpi) {
+      for (long long r = row0 + r_in; r < row1; r += rpi) {
+        const long long off = r * C + 8 * v;
+        float fy[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s0[i] += fy[i]; s1[i] = fmaf(fy[i], fy[i], s1[i]); }
+        } else {
+          float g[8];
+          unpack8(*reinterpret_cast<const uint4*>(da + off), g);
+          if (MODE == 2) {
+            float fa[8];
+            unpack8(*reinterpret_cast<const uint4*>(act + off), fa);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = (!relu || fa[i] > 0.f) ? g[i] : 0.f;
+            *reinterpret_cast<uint4*>(gout + off) = pack8(g);
+          } else if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s0[i] += g[i];
+            s1[i] = fmaf(g[i], (fy[i] - mu[i]) * rs[i], s1[i]);
+          }
+        }
+      }
+    }
+    // reduce over the rpi row-threads that share this vector lane
+    if (r_in < rpi) {
+      float* dst = red + ((size_t)r_in * vl + v0) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dst[i] = s0[i]; dst[8 + i] = s1[i]; }
+    }
+    __syncthreads();
+    if (r_in == 0) {
+      float a0[8], a1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+      for (int rr = 0; rr < rpi; ++rr) {
+        const float* src = red + ((size_t)rr * vl + v0) * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] += src[i]; a1[i] += src[8 + i]; }
+      }
+      float* p0 = partial + (size_t)blockIdx.x * 2 * C + 8 * v;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p0[i] = a0[i]; p0[C + i] = a1[i]; }
+    }
+    __syncthreads();
+  }
+}
+
+// Forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running stats.
+__global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int nblocks, int C, long long rows, float eps,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
+                                  float* __restrict__ shift, float* __restrict__ running_mean,
+                                  float* __restrict__ running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[(size_t)b * 2 * C + c];
+    q += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  const double m = s / (double)rows;
+  double var = q / (double)rows - m * m;
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)m;
+  rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// Backward finalize: dbeta, dgamma (+ the two per-channel coefficients the apply pass needs).
+__global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int nblocks, int C, long long rows,
+                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                  float* __restrict__ coef /*[2][C]: dbeta/M, dgamma/M*/) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[(size_t)b * 2 * C + c];
+    q += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)q;
+  coef[c] = (float)(s / (double)rows);
+  coef[C + c] = (float)(q / (double)rows);
+}
+
+// a = [relu](y*scale + shift (+ residual))
+__global__ void __launch_bounds__(kBnThreads)
+k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
+           const float* __restrict__ scale, const float* __restrict__ shift, int relu, long long nvec, int V,
+           __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(y)[i], f);
+    const float4 s0 = reinterpret_cast<const float4*>(scale)[2 * v], s1 = reinterpret_cast<const float4*>(scale)[2 * v + 1];
+    const float4 b0 = reinterpret_cast<const float4*>(shift)[2 * v], b1 = reinterpret_cast<const float4*>(shift)[2 * v + 1];
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+    if (residual) {
+      float r[8];
+      unpack8(reinterpret_cast<const uint4*>(residual)[i], r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+
+// dy = scale * (g - dbeta/M - xhat * dgamma/M);  g = da * relu' (recomputed) or the stored g.
+__global__ void __launch_bounds__(kBnThreads)
+k_bn_bwd_apply(const __nv_bfloat16* __restrict__ g_or_da, const __nv_bfloat16* __restrict__ y,
+               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+               const float* __restrict__ shift, const float* __restrict__ coef, int relu_recompute, long long nvec,
+               int V, int C, __nv_bfloat16* __restrict__ dy) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % V) * 8;
+    float g[8], fy[8], o[8];
+    unpack8(reinterpret_cast<const uint4*>(g_or_da)[i], g);
+    unpack8(reinterpret_cast<const uint4*>(y)[i], fy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sc = scale[c0 + k];
+      if (relu_recompute && !(fmaf(fy[k], sc, shift[c0 + k]) > 0.f)) g[k] = 0.f;
+      const float xhat = (fy[k] - mean[c0 + k]) * rstd[c0 + k];
+      o[k] = sc * (g[k] - coef[c0 + k] - xhat * coef[C + c0 + k]);
+    }
+    reinterpret_cast<uint4*>(dy)[i] = pack8(o);
+  }
+}
+
+static int colsum_blocks(long long rows, int C, long long* rows_per_block) {
+  const int V = C >> 3;
+  const int vl = V < kBnThreads ? V : kBnThreads;
+  const int rpi = kBnThreads / vl;
+  long long target = 148 * 6;                         // ~6 resident blocks per SM
+  long long rpb = (rows + target - 1) / target;
+  rpb = (rpb + rpi - 1) / rpi * rpi;
+  if (rpb < rpi) rpb = rpi;
+  *rows_per_block = rpb;
+  return (int)((rows + rpb - 1) / rpb);
+}
+
+static size_t colsum_smem(int C) {
+  const int V = C >> 3;
+  const int vl = V < kBnThreads ? V : kBnThreads;
+  const int rpi = kBnThreads / vl;
+  return (size_t)rpi * vl * 16 * sizeof(float);
+}
+
+}  // namespace rigl
+
+using namespace rigl;
+
+extern "C" size_t rigl_bn_workspace_bytes(int64_t rows, int channels) {
+  if (rows <= 0 || channels <= 0) return 0;
+  long long rpb;
+  const int nb = colsum_blocks(rows, channels, &rpb);
+  return (size_t)nb * 2 * channels * sizeof(float) + 256;
+}
+
+extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const float* gamma, const float* beta,
+                                     int64_t rows, int channels, float eps, float momentum, int relu,
+                                     float* running_mean, float* running_var, float* save_mean, float* save_rstd,
+                                     float* save_scale, float* save_shift, void* out, void* ws, size_t ws_bytes,
+                                     void* stream_) {
+  RIGL_REQUIRE(y && gamma && beta && save_mean && save_rstd && save_scale && save_shift && out && ws,
+               "rigl_bn_forward_train: null argument");
+  RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, "rigl_bn_forward_train: channels must be a multiple of 8");
+  RIGL_REQUIRE(aligned16(y) && aligned16(out) && aligned16(residual) && aligned16(save_scale) && aligned16(save_shift),
+               "rigl_bn_forward_train: tensors must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream_;
+  long long rpb;
+  const int nb = colsum_blocks(rows, channels, &rpb);
+  if (ws_bytes < (size_t)nb * 2 * channels * sizeof(float)) {
+    set_error("rigl_bn_forward_train: workspace too small");
+    return RIGL_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(ws);
+  k_bn_colsum<0><<<nb, kBnThreads, colsum_smem(channels), s>>>(
+      (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels, rpb,
+      partial);
+  RIGL_LAUNCH_CHECK("k_bn_colsum<0>");
+  k_bn_finalize_fwd<<<(channels + 127) / 128, 128, 0, s>>>(partial, nb, channels, rows, eps, gamma, beta, save_mean,
+                                                           save_rstd, save_scale, save_shift, running_mean,
+                                                           running_var, momentum);
+  RIGL_LAUNCH_CHECK("k_bn_finalize_fwd");
+  const long long nvec = rows * (channels / 8);
+  long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)residual,
+                                                     save_scale, save_shift, relu, nvec, channels / 8,
+                                                     (__nv_bfloat16*)out);
+  RIGL_LAUNCH_CHECK("k_bn_apply");
+  return RIGL_OK;
+}
+
+extern "C" int rigl_bn_apply(const void* y, const void* residual, const float* scale, const float* shift,
+                             int64_t rows, int channels, int relu, void* out, void* stream_) {
+  RIGL_REQUIRE(y && scale && shift && out && rows > 0 && channels > 0 && channels % 8 == 0,
+               "rigl_bn_apply: bad arguments");
+  const long long nvec = rows * (channels / 8);
+  long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)y, (const __nv_bfloat16*)residual, scale, shift, relu, nvec, channels / 8,
+      (__nv_bfloat16*)out);
+  RIGL_LAUNCH_CHECK("k_bn_apply");
+  return RIGL_OK;
+}
+
+extern "C" int rigl_bn_backward(const void* da, const void* y, const void* act, const float* save_mean,
+                                const float* save_rstd, const float* save_scale, const float* save_shift,
+                                int64_t rows, int channels, int relu, void* dy, void* dresidual, float* dgamma,
+                                float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+  RIGL_REQUIRE(da && y && save_mean && save_rstd && save_scale && save_shift && dy && dgamma && dbeta && ws,
+               "rigl_bn_backward: null argument");
+  RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, "rigl_bn_backward: channels must be a multiple of 8");
+  RIGL_REQUIRE((dresidual == nullptr) || (act != nullptr), "rigl_bn_backward: the residual form needs the saved output");
+  cudaStream_t s = (cudaStream_t)stream_;
+  long long rpb;
+  const int nb = colsum_blocks(rows, channels, &rpb);
+  const size_t need = (size_t)nb * 2 * channels * sizeof(float) + 2 * channels * sizeof(float);
+  if (ws_bytes < need) {
+    set_error("rigl_bn_backward: workspace too small");
+    return RIGL_ERR_WORKSPACE;
+  }
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + (size_t)nb * 2 * channels;
+  const bool residual_form = dresidual != nullptr;
+  if (residual_form) {
+    k_bn_colsum<2><<<nb, kBnThreads, colsum_smem(channels), s>>>(
+        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, (const __nv_bfloat16*)act, (__nv_bfloat16*)dresidual,
+        save_mean, save_rstd, save_scale, save_shift, relu, rows, channels, rpb, partial);
+    RIGL_LAUNCH_CHECK("k_bn_colsum<2>");
+  } else {
+    k_bn_colsum<1><<<nb, kBnThreads, colsum_smem(channels), s>>>(
+        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, nullptr, nullptr, save_mean, save_rstd, save_scale,
+        save_shift, relu, rows, channels, rpb, partial);
+    RIGL_LAUNCH_CHECK("k_bn_colsum<1>");
+  }
+  k_bn_finalize_bwd<<<(channels + 127) / 128, 128, 0, s>>>(partial, nb, channels, rows, dgamma, dbeta, coef);
+  RIGL_LAUNCH_CHECK("k_bn_finalize_bwd");
+  const long long nvec = rows * (channels / 8);
+  long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_bn_bwd_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>(
+      (const __nv_bfloat16*)(residual_form ? dresidual : da), (const __nv_bfloat16*)y, save_mean, save_rstd,
+      save_scale, save_shift, coef, (!residual_form && relu) ? 1 : 0, nvec, channels / 8, channels,
+      (__nv_bfloat16*)dy);
+  RIGL_LAUNCH_CHECK("k_bn_bwd_apply");
+  return RIGL_OK;
+}

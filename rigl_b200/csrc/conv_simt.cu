@@ -96,34 +96,63 @@ __global__ void k_simt_wgrad(ConvGeom g, const __nv_bfloat16* __restrict__ x,
   atomicAdd(dw + o, acc);
 }
 
-// out[p][(kh*k+kw)*cin + ci] = x[pix(p, kh, kw), ci]; one thread per (pixel, kh) copies k*cin
-// contiguous input elements; the kh == 0 thread also zeroes the pad columns.
-__global__ void k_im2col(ConvGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                         int64_t out_pitch) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t p = t / g.ksize;
-  const int kh = (int)(t % g.ksize);
-  if (p >= g.out_pixels()) return;
-  const int wo = (int)(p % g.out_w);
-  const int ho = (int)((p / g.out_w) % g.out_h);
-  const int n = (int)(p / ((int64_t)g.out_w * g.out_h));
-  const int hi = ho * g.stride + kh - g.pad;
-  __nv_bfloat16* dst = out + p * out_pitch + (int64_t)kh * g.ksize * g.cin;
+// Patch matrix: out[p][(kh*k+kw)*cin + ci] = x[pix(p, kh, kw), ci].
+// One block = kTP consecutive output pixels of one output row: the k input rows they touch
+// are staged in shared memory with coalesced reads, then every thread emits 16-byte chunks
+// of the output rows, so the (large) write stream is fully coalesced.
+constexpr int kTP = 32;
+__global__ void __launch_bounds__(256)
+k_im2col(ConvGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t out_pitch) {
+  extern __shared__ __nv_bfloat16 sm[];
+  const int segs = (g.out_w + kTP - 1) / kTP;
+  const int seg = blockIdx.x % segs;
+  const int ho = (blockIdx.x / segs) % g.out_h;
+  const int n = blockIdx.x / (segs * g.out_h);
+  const int wo0 = seg * kTP;
+  const int npix = min(kTP, g.out_w - wo0);
+  const int span = (kTP - 1) * g.stride + g.ksize;
+  const int rowlen = span * g.cin;
+  const int wi0 = wo0 * g.stride - g.pad;
   const __nv_bfloat16 zero = __float2bfloat16(0.f);
-  for (int kw = 0; kw < g.ksize; ++kw) {
-    const int wi = wo * g.stride + kw - g.pad;
-    const bool ok = hi >= 0 && hi < g.in_h && wi >= 0 && wi < g.in_w;
-    const __nv_bfloat16* src = x + (((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch;
-    for (int ci = 0; ci < g.cin; ++ci) dst[kw * g.cin + ci] = ok ? src[ci] : zero;
+  for (int idx = threadIdx.x; idx < g.ksize * rowlen; idx += blockDim.x) {
+    const int kh = idx / rowlen, r = idx - kh * rowlen;
+    const int wi = wi0 + r / g.cin, c = r % g.cin;
+    const int hi = ho * g.stride + kh - g.pad;
+    __nv_bfloat16 v = zero;
+    if (hi >= 0 && hi < g.in_h && wi >= 0 && wi < g.in_w)
+      v = x[(((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch + c];
+    sm[idx] = v;
   }
-  if (kh == 0)
-    for (int64_t c = (int64_t)g.taps() * g.cin; c < out_pitch; ++c) out[p * out_pitch + c] = zero;
+  __syncthreads();
+  const int kc = g.ksize * g.cin;                 // elements per kh segment
+  const int K = g.ksize * kc;
+  const int cpr = (int)(out_pitch / 8);           // 16-byte chunks per output row
+  const int64_t p0 = ((int64_t)n * g.out_h + ho) * g.out_w + wo0;
+  for (int q = threadIdx.x; q < npix * cpr; q += blockDim.x) {
+    const int pl = q / cpr, j = q - pl * cpr;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = 8 * j + e;
+      __nv_bfloat16 t = zero;
+      if (kk < K) {
+        const int kh = kk / kc, r = kk - kh * kc;
+        t = sm[kh * rowlen + pl * g.stride * g.cin + r];
+      }
+      v[e] = t;
+    }
+    *reinterpret_cast<uint4*>(out + (p0 + pl) * out_pitch + 8 * j) = *reinterpret_cast<const uint4*>(v);
+  }
 }
 
 int simt_im2col(const ConvGeom& g, const void* x, void* out, int64_t out_pitch, cudaStream_t s) {
-  const int64_t threads = g.out_pixels() * g.ksize;
-  k_im2col<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)out,
-                                                             out_pitch);
+  RIGL_REQUIRE(out_pitch % 8 == 0 && aligned16(out), "rigl_im2col_nhwc: out_pitch must be a multiple of 8");
+  const int segs = (g.out_w + kTP - 1) / kTP;
+  const int span = (kTP - 1) * g.stride + g.ksize;
+  const size_t smem = (size_t)g.ksize * span * g.cin * sizeof(__nv_bfloat16);
+  RIGL_REQUIRE(smem <= 48 * 1024, "rigl_im2col_nhwc: patch rows too large for shared memory (%zu B)", smem);
+  const int64_t blocks = (int64_t)g.batch * g.out_h * segs;
+  k_im2col<<<(unsigned)blocks, 256, smem, s>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, out_pitch);
   RIGL_LAUNCH_CHECK("k_im2col");
   return RIGL_OK;
 }

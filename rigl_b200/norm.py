@@ -1,0 +1,97 @@
+"""Fused batch-norm + ReLU (+ residual add) on NHWC bf16 activations.
+
+Host mirror of `batch_norm_relu(inputs, is_training, relu, init_zero)`
+(rigl/imagenet_resnet/resnet_model.py:41-80; BATCH_NORM_DECAY 0.9, EPSILON 1e-5) and of the
+`relu(inputs + shortcut)` tail of the bottleneck block (:501), backed by csrc/bn.cu.
+Not a masked op in the reference -- it is the HBM-bound glue between the masked convs
+(SURVEY 8f row 1), so it gets streaming kernels instead of tensor cores.
+"""
+import torch
+from torch import nn
+
+from . import _cabi
+from .layers import _timed, _workspace
+
+
+def _p(t):
+  return None if t is None else t.data_ptr()
+
+
+class _BNFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, y, gamma, beta, residual, mod):
+    n, c, h, w = y.shape
+    rows = n * h * w
+    dev = y.device
+    out = torch.empty_like(y, memory_format=torch.channels_last)
+    save = torch.empty((4, c), dtype=torch.float32, device=dev)      # mean, rstd, scale, shift
+    ws = _workspace(dev, _cabi.lib().rigl_bn_workspace_bytes(rows, c) + 8 * c + 256)
+
+    def run():
+      _cabi.check(_cabi.lib().rigl_bn_forward_train(
+          y.data_ptr(), _p(residual), gamma.data_ptr(), beta.data_ptr(), rows, c, mod.eps, mod.momentum,
+          int(mod.relu), mod.running_mean.data_ptr(), mod.running_var.data_ptr(), save[0].data_ptr(),
+          save[1].data_ptr(), save[2].data_ptr(), save[3].data_ptr(), out.data_ptr(), ws.data_ptr(),
+          ws.numel(), _cabi.stream_ptr()), 'rigl_bn_forward_train')
+    _timed('bn_fwd', mod, run)
+    ctx.mod, ctx.has_res = mod, residual is not None
+    ctx.save_for_backward(y, out if residual is not None else None, save)
+    return out
+
+  @staticmethod
+  def backward(ctx, da):
+    y, act, save = ctx.saved_tensors
+    mod = ctx.mod
+    n, c, h, w = y.shape
+    rows = n * h * w
+    da = da.contiguous(memory_format=torch.channels_last)
+    if da.dtype != torch.bfloat16:
+      da = da.to(torch.bfloat16)
+    dy = torch.empty_like(y, memory_format=torch.channels_last)
+    dres = torch.empty_like(y, memory_format=torch.channels_last) if ctx.has_res else None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
+    ws = _workspace(y.device, _cabi.lib().rigl_bn_workspace_bytes(rows, c) + 8 * c + 256)
+
+    def run():
+      _cabi.check(_cabi.lib().rigl_bn_backward(
+          da.data_ptr(), y.data_ptr(), _p(act), save[0].data_ptr(), save[1].data_ptr(), save[2].data_ptr(),
+          save[3].data_ptr(), rows, c, int(mod.relu), dy.data_ptr(), _p(dres), dgb[0].data_ptr(),
+          dgb[1].data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr()), 'rigl_bn_backward')
+    _timed('bn_bwd', mod, run)
+    return dy, dgb[0], dgb[1], dres, None
+
+
+class FusedBatchNormReLU(nn.Module):
+  """y -> [relu](BN(y) [+ residual]); training mode uses batch statistics."""
+
+  def __init__(self, channels, relu=True, init_zero=False, eps=1e-5, decay=0.9, device='cuda', name=None):
+    super(FusedBatchNormReLU, self).__init__()
+    if channels % 8:
+      raise ValueError('FusedBatchNormReLU needs channels % 8 == 0')
+    self.channels, self.relu, self.eps, self.momentum = channels, bool(relu), float(eps), 1.0 - float(decay)
+    self.scope = name or 'batch_normalization'
+    self.weight = nn.Parameter(torch.zeros(channels, device=device) if init_zero
+                               else torch.ones(channels, device=device))
+    self.bias = nn.Parameter(torch.zeros(channels, device=device))
+    self.register_buffer('running_mean', torch.zeros(channels, device=device))
+    self.register_buffer('running_var', torch.ones(channels, device=device))
+
+  def forward(self, y, residual=None):
+    if y.dim() != 4 or y.shape[1] != self.channels:
+      raise ValueError('expected [N,%d,H,W]' % self.channels)
+    y = y.contiguous(memory_format=torch.channels_last)
+    if y.dtype != torch.bfloat16:
+      y = y.to(torch.bfloat16)
+    if residual is not None:
+      residual = residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    if self.training:
+      return _BNFn.apply(y, self.weight, self.bias, residual, self)
+    scale = self.weight.detach() * torch.rsqrt(self.running_var + self.eps)
+    shift = self.bias.detach() - self.running_mean * scale
+    out = torch.empty_like(y, memory_format=torch.channels_last)
+    n, c, h, w = y.shape
+    _cabi.check(_cabi.lib().rigl_bn_apply(y.data_ptr(), _p(residual), scale.data_ptr(), shift.data_ptr(),
+                                          n * h * w, c, int(self.relu), out.data_ptr(), _cabi.stream_ptr()),
+                'rigl_bn_apply')
+    return out

@@ -6,8 +6,8 @@ that the masked conv/linear kernels and the RigL update run on:
   ResNet50   rigl/imagenet_resnet/resnet_model.py:396-731 (v1.5: stride on the 3x3;
              BN after every conv, zero-init gamma on the last BN of a block)
   MnistFC    rigl/mnist/mnist_train_eval.py:112-160 (784-300-100-10, all masked)
-BN / ReLU / pooling / loss are NOT on the masked path (the reference never masks
-them) and run on stock PyTorch kernels over channels_last bf16 tensors.
+BN+ReLU(+residual) run on the fused streaming kernels of csrc/bn.cu (SURVEY 8f row 1);
+pooling / loss are stock PyTorch kernels over channels_last bf16 tensors.
 """
 import numpy as np
 import torch
@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from . import pruning
 from . import sparse_utils
 from .layers import SparseConv2d, SparseLinear, variance_scaling_
+from .norm import FusedBatchNormReLU
 from .sparse_optimizers import SparseRigLOptimizer
 from .sparse_optimizers_base import GlobalStep
 
@@ -24,20 +25,10 @@ BATCH_NORM_DECAY = 0.9
 BATCH_NORM_EPSILON = 1e-5
 
 
-class _BNReLU(nn.Module):
-  """batch_norm_relu (resnet_model.py:41-80)."""
-
-  def __init__(self, channels, relu=True, init_zero=False, device='cuda'):
-    super(_BNReLU, self).__init__()
-    self.bn = nn.BatchNorm2d(channels, eps=BATCH_NORM_EPSILON, momentum=1.0 - BATCH_NORM_DECAY,
-                             device=device)
-    if init_zero:
-      nn.init.zeros_(self.bn.weight)
-    self.relu = relu
-
-  def forward(self, x):
-    x = self.bn(x)
-    return F.relu(x, inplace=True) if self.relu else x
+def _BNReLU(channels, relu=True, init_zero=False, device='cuda'):
+  """batch_norm_relu (resnet_model.py:41-80) on the fused streaming kernels (csrc/bn.cu)."""
+  return FusedBatchNormReLU(channels, relu=relu, init_zero=init_zero, eps=BATCH_NORM_EPSILON,
+                            decay=BATCH_NORM_DECAY, device=device)
 
 
 class _Bottleneck(nn.Module):
@@ -55,14 +46,14 @@ class _Bottleneck(nn.Module):
     self.conv2 = mk(filters, filters, 3, strides, 'bottleneck_2_%s' % name)
     self.bn2 = _BNReLU(filters, device=device)
     self.conv3 = mk(filters, 4 * filters, 1, 1, 'bottleneck_3_%s' % name)
-    self.bn3 = _BNReLU(4 * filters, relu=False, init_zero=True, device=device)
+    # last BN of the block: zero-init gamma; the residual add + final ReLU are fused into it
+    self.bn3 = _BNReLU(4 * filters, relu=True, init_zero=True, device=device)
 
   def forward(self, x):
     shortcut = x if self.proj is None else self.proj_bn(self.proj(x))
     y = self.bn1(self.conv1(x))
     y = self.bn2(self.conv2(y))
-    y = self.bn3(self.conv3(y))
-    return F.relu(y + shortcut, inplace=True)
+    return self.bn3(self.conv3(y), residual=shortcut)          # relu(BN(conv3) + shortcut)
 
 
 class ResNet50(nn.Module):

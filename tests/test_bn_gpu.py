@@ -1,0 +1,92 @@
+"""Fused BN(+ReLU,+residual) kernels vs a float64 restatement of batch_norm_relu
+(rigl/imagenet_resnet/resnet_model.py:41-80) on the same bf16-rounded inputs.
+Tolerances: bf16 outputs within 1 bf16 ulp of the fp64 result (+ tiny absolute slack);
+fp32 reductions (dgamma, dbeta, running stats) rel 2e-3 of the reduction scale."""
+import numpy as np
+import pytest
+import torch
+
+from rigl_b200.norm import FusedBatchNormReLU
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _bf(a):
+  return torch.from_numpy(np.asarray(a, np.float32)).to(torch.bfloat16)
+
+
+def _nhwc_to_dev(a):
+  return _bf(a).permute(0, 3, 1, 2).to(DEV).contiguous(memory_format=torch.channels_last)
+
+
+def _close_bf16(got, want, what):
+  got = got.detach().float().cpu().numpy().astype(np.float64)
+  scale = np.abs(want).max() + 1e-30
+  tol = np.abs(want) * 2.0 ** -7 + scale * 2.0 ** -9
+  err = np.abs(got - want)
+  assert (err <= tol).all(), '%s: max err %g at scale %g (%d bad)' % (what, err.max(), scale, (err > tol).sum())
+
+
+@pytest.mark.parametrize('shape', [(4, 8, 8, 64), (2, 7, 7, 2048), (3, 5, 9, 24), (16, 28, 28, 128), (2, 3, 3, 8)])
+@pytest.mark.parametrize('relu,residual', [(True, False), (False, False), (True, True)])
+def test_bn_forward_backward(shape, relu, residual):
+  n, h, w, c = shape
+  rng = np.random.RandomState(c + n)
+  y_np = _bf(rng.standard_normal(shape) * 1.7 + 0.3).float().numpy().astype(np.float64)
+  r_np = _bf(rng.standard_normal(shape)).float().numpy().astype(np.float64) if residual else None
+  da_np = _bf(rng.standard_normal(shape)).float().numpy().astype(np.float64)
+  gamma = rng.rand(c) + 0.5
+  beta = rng.standard_normal(c) * 0.2
+  bn = FusedBatchNormReLU(c, relu=relu, device=DEV)
+  with torch.no_grad():
+    bn.weight.copy_(torch.from_numpy(gamma.astype(np.float32)))
+    bn.bias.copy_(torch.from_numpy(beta.astype(np.float32)))
+  gamma, beta = bn.weight.detach().cpu().double().numpy(), bn.bias.detach().cpu().double().numpy()
+  y = _nhwc_to_dev(y_np).requires_grad_(True)
+  r = _nhwc_to_dev(r_np).requires_grad_(True) if residual else None
+  out = bn(y, residual=r)
+  out.backward(_nhwc_to_dev(da_np))
+  # ---- float64 reference
+  m = n * h * w
+  mean = y_np.reshape(m, c).mean(0)
+  var = y_np.reshape(m, c).var(0)
+  rstd = 1.0 / np.sqrt(var + 1e-5)
+  xhat = (y_np - mean) * rstd
+  z = gamma * xhat + beta + (r_np if residual else 0.0)
+  want = np.maximum(z, 0) if relu else z
+  _close_bf16(out.permute(0, 2, 3, 1), want, 'forward')
+  # relu mask from the kernel's own (bf16) output avoids counting sign flips at |z| ~ 0 as errors
+  a_got = out.detach().permute(0, 2, 3, 1).float().cpu().numpy()
+  g = da_np * ((a_got > 0) if relu else 1.0)
+  dbeta = g.reshape(m, c).sum(0)
+  dgamma = (g * xhat).reshape(m, c).sum(0)
+  dy = gamma * rstd * (g - dbeta / m - xhat * dgamma / m)
+  _close_bf16(y.grad.permute(0, 2, 3, 1), dy, 'dy')
+  red_scale = np.abs(g).sum(axis=(0, 1, 2)).max() + 1e-30
+  assert np.abs(bn.bias.grad.cpu().double().numpy() - dbeta).max() <= 2e-3 * red_scale
+  assert np.abs(bn.weight.grad.cpu().double().numpy() - dgamma).max() <= 2e-3 * red_scale * 3
+  if residual:
+    _close_bf16(r.grad.permute(0, 2, 3, 1), g, 'dresidual')
+  assert np.allclose(bn.running_mean.cpu().numpy(), 0.1 * mean, rtol=1e-3, atol=1e-4)
+  assert np.allclose(bn.running_var.cpu().numpy(), 0.9 + 0.1 * var * m / (m - 1), rtol=1e-3, atol=1e-4)
+
+
+def test_bn_eval_mode_and_errors():
+  bn = FusedBatchNormReLU(16, relu=True, device=DEV)
+  with torch.no_grad():
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.uniform_(0.5, 1.5)
+    bn.bias.normal_()
+  bn.eval()
+  x = torch.randn(2, 16, 5, 5, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  got = bn(x).float()
+  want = torch.relu((x.float() - bn.running_mean[None, :, None, None]) *
+                    torch.rsqrt(bn.running_var + 1e-5)[None, :, None, None] * bn.weight[None, :, None, None] +
+                    bn.bias[None, :, None, None])
+  assert float((got - want).abs().max()) <= 2 ** -7 * float(want.abs().max()) + 1e-3
+  with pytest.raises(ValueError):
+    FusedBatchNormReLU(12, device=DEV)
+  with pytest.raises(ValueError):
+    bn(torch.zeros(2, 8, 5, 5, device=DEV))

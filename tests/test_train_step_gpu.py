@@ -21,8 +21,7 @@ def _reference_forward(model, x):
     sc = t if blk.proj is None else blk.proj_bn(conv(blk.proj, t))
     y = blk.bn1(conv(blk.conv1, t))
     y = blk.bn2(conv(blk.conv2, y))
-    y = blk.bn3(conv(blk.conv3, y))
-    t = F.relu(y + sc)
+    t = blk.bn3(conv(blk.conv3, y), residual=sc)
   t = t.mean(dim=(2, 3))
   fc = model.final_dense
   return t.float() @ (fc.weight.detach() * fc.mask.to_dense()).to(torch.bfloat16).float() + fc.bias.detach()
@@ -46,7 +45,7 @@ def test_forward_matches_stock_torch_convs():
   model = workloads.ResNet50(device=DEV)
   workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=1)
   for blk in model.blocks:                      # make the residual branch non-trivial
-    torch.nn.init.ones_(blk.bn3.bn.weight)
+    torch.nn.init.ones_(blk.bn3.weight)
   model.eval()                                  # BN in inference mode: deterministic comparison
   x = torch.randn(4, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   with torch.no_grad():
