@@ -70,6 +70,7 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
       }
     }
     if (r_in < rpi) {
+#pragma unroll 4
       for (long long r = row0 + r_in; r < row1; r += rpi) {
         const long long off = r * C + 8 * v;
         float fy[8];
@@ -122,19 +123,36 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
   }
 }
 
-// Forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running stats.
-__global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int nblocks, int C, long long rows, float eps,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
-                                  float* __restrict__ shift, float* __restrict__ running_mean,
-                                  float* __restrict__ running_var, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Sums partial[b][which][c] over b for a 32-channel slab: blockDim = (32 channels, 32 slices).
+__device__ __forceinline__ void slab_sums(const float* __restrict__ partial, int nblocks, int C, int c,
+                                          double* s_out, double* q_out) {
+  __shared__ double sm_s[32][33], sm_q[32][33];
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[(size_t)b * 2 * C + c];
-    q += (double)partial[(size_t)b * 2 * C + C + c];
+  if (c < C)
+    for (int b = threadIdx.y; b < nblocks; b += 32) {
+      s += (double)partial[(size_t)b * 2 * C + c];
+      q += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+  sm_s[threadIdx.y][threadIdx.x] = s;
+  sm_q[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int j = 1; j < 32; ++j) { s += sm_s[j][threadIdx.x]; q += sm_q[j][threadIdx.x]; }
+    *s_out = s;
+    *q_out = q;
   }
+}
+
+// Forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running stats.
+__global__ void __launch_bounds__(1024)
+k_bn_finalize_fwd(const float* __restrict__ partial, int nblocks, int C, long long rows, float eps,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean,
+                  float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift,
+                  float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  slab_sums(partial, nblocks, C, c, &s, &q);
+  if (threadIdx.y != 0 || c >= C) return;
   const double m = s / (double)rows;
   double var = q / (double)rows - m * m;
   if (var < 0.0) var = 0.0;
@@ -151,21 +169,22 @@ __global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int nblocks
   }
 }
 
-// Backward finalize: dbeta, dgamma (+ the two per-channel coefficients the apply pass needs).
-__global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int nblocks, int C, long long rows,
-                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                  float* __restrict__ coef /*[2][C]: dbeta/M, dgamma/M*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[(size_t)b * 2 * C + c];
-    q += (double)partial[(size_t)b * 2 * C + C + c];
-  }
+// Backward finalize: dbeta, dgamma and the per-channel affine form of the input gradient
+//   dy = scale*g + P*y + Q,  P = -scale*rstd*dgamma/M,  Q = scale*(rstd*mean*dgamma/M - dbeta/M).
+__global__ void __launch_bounds__(1024)
+k_bn_finalize_bwd(const float* __restrict__ partial, int nblocks, int C, long long rows,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef /*[2][C]: P, Q*/) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  slab_sums(partial, nblocks, C, c, &s, &q);
+  if (threadIdx.y != 0 || c >= C) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
-  coef[c] = (float)(s / (double)rows);
-  coef[C + c] = (float)(q / (double)rows);
+  const double c0 = s / (double)rows, c1 = q / (double)rows;
+  const double sc = (double)scale[c], r = (double)rstd[c], m = (double)mean[c];
+  coef[c] = (float)(-sc * r * c1);
+  coef[C + c] = (float)(sc * (r * m * c1 - c0));
 }
 
 // a = [relu](y*scale + shift (+ residual))
@@ -198,25 +217,34 @@ k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
   }
 }
 
-// dy = scale * (g - dbeta/M - xhat * dgamma/M);  g = da * relu' (recomputed) or the stored g.
+__device__ __forceinline__ void load8f(const float* __restrict__ p, int v, float (&o)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[2 * v], b = reinterpret_cast<const float4*>(p)[2 * v + 1];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// dy = scale*g + P*y + Q;  g = da * relu' (recomputed from y) or the stored g.
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_bwd_apply(const __nv_bfloat16* __restrict__ g_or_da, const __nv_bfloat16* __restrict__ y,
-               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
-               const float* __restrict__ shift, const float* __restrict__ coef, int relu_recompute, long long nvec,
-               int V, int C, __nv_bfloat16* __restrict__ dy) {
+               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
+               int relu_recompute, long long nvec, int V, int C, __nv_bfloat16* __restrict__ dy) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % V) * 8;
-    float g[8], fy[8], o[8];
+    const int v = (int)(i % V);
+    float g[8], fy[8], o[8], sc[8], P[8], Q[8];
     unpack8(reinterpret_cast<const uint4*>(g_or_da)[i], g);
     unpack8(reinterpret_cast<const uint4*>(y)[i], fy);
+    load8f(scale, v, sc);
+    load8f(coef, v, P);
+    load8f(coef + C, v, Q);
+    if (relu_recompute) {
+      float sh[8];
+      load8f(shift, v, sh);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float sc = scale[c0 + k];
-      if (relu_recompute && !(fmaf(fy[k], sc, shift[c0 + k]) > 0.f)) g[k] = 0.f;
-      const float xhat = (fy[k] - mean[c0 + k]) * rstd[c0 + k];
-      o[k] = sc * (g[k] - coef[c0 + k] - xhat * coef[C + c0 + k]);
+      for (int k = 0; k < 8; ++k)
+        if (!(fmaf(fy[k], sc[k], sh[k]) > 0.f)) g[k] = 0.f;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], g[k], fmaf(P[k], fy[k], Q[k]));
     reinterpret_cast<uint4*>(dy)[i] = pack8(o);
   }
 }
@@ -273,9 +301,9 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels, rpb,
       partial);
   RIGL_LAUNCH_CHECK("k_bn_colsum<0>");
-  k_bn_finalize_fwd<<<(channels + 127) / 128, 128, 0, s>>>(partial, nb, channels, rows, eps, gamma, beta, save_mean,
-                                                           save_rstd, save_scale, save_shift, running_mean,
-                                                           running_var, momentum);
+  k_bn_finalize_fwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, nb, channels, rows, eps, gamma, beta,
+                                                                  save_mean, save_rstd, save_scale, save_shift,
+                                                                  running_mean, running_var, momentum);
   RIGL_LAUNCH_CHECK("k_bn_finalize_fwd");
   const long long nvec = rows * (channels / 8);
   long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
@@ -331,15 +359,15 @@ extern "C" int rigl_bn_backward(const void* da, const void* y, const void* act, 
         save_shift, relu, rows, channels, rpb, partial);
     RIGL_LAUNCH_CHECK("k_bn_colsum<1>");
   }
-  k_bn_finalize_bwd<<<(channels + 127) / 128, 128, 0, s>>>(partial, nb, channels, rows, dgamma, dbeta, coef);
+  k_bn_finalize_bwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, nb, channels, rows, save_mean, save_rstd,
+                                                                  save_scale, dgamma, dbeta, coef);
   RIGL_LAUNCH_CHECK("k_bn_finalize_bwd");
   const long long nvec = rows * (channels / 8);
   long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_bn_bwd_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>(
-      (const __nv_bfloat16*)(residual_form ? dresidual : da), (const __nv_bfloat16*)y, save_mean, save_rstd,
-      save_scale, save_shift, coef, (!residual_form && relu) ? 1 : 0, nvec, channels / 8, channels,
-      (__nv_bfloat16*)dy);
+      (const __nv_bfloat16*)(residual_form ? dresidual : da), (const __nv_bfloat16*)y, save_scale, save_shift, coef,
+      (!residual_form && relu) ? 1 : 0, nvec, channels / 8, channels, (__nv_bfloat16*)dy);
   RIGL_LAUNCH_CHECK("k_bn_bwd_apply");
   return RIGL_OK;
 }

@@ -130,7 +130,7 @@ class TrainHarness(object):
     self.model = model
     self.label_smoothing = label_smoothing
     self.inner = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, nesterov=True,
-                                 weight_decay=weight_decay)
+                                 weight_decay=weight_decay, foreach=True)
     self.opt = optimizer_cls(self.inner, begin_step, end_step, frequency, drop_fraction=drop_fraction,
                              drop_fraction_anneal=drop_fraction_anneal,
                              use_tpu=data_parallel is not None).bind(model.registry)
