@@ -60,7 +60,7 @@ class SparseStaticOptimizer(SparseSETOptimizer):
     return mask.to_dense().view(-1)
 
   def _layer_spec(self, mask, weights, noise_std, score_drop=None, score_grow=None,
-                  reinit_when_same=True):
+                  reinit_when_same=True, noise=None):
     return super(SparseStaticOptimizer, self)._layer_spec(
         mask, weights, noise_std, score_drop=score_drop, score_grow=score_grow,
-        reinit_when_same=True)
+        reinit_when_same=True, noise=noise)

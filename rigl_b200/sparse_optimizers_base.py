@@ -240,10 +240,36 @@ class SparseSETOptimizerBase(object):
     return False
 
   def mask_update_op(self):
-    """Updates every (mask, weights) pair -- one batched launch sequence."""
+    """Updates every (mask, weights) pair -- one batched launch sequence.  The drop-score
+    noise of ALL layers is one keyed draw over a flat buffer (per-layer views), so the host
+    cost does not scale with the layer count."""
     pairs = list(zip(self.get_masks(), self.get_weights()))
-    if pairs:
-      self._run_update([self._layer_spec(m, w, self.noise_std) for m, w in pairs])
+    if not pairs:
+      return
+    self._slot_names_cache = self.get_slot_names()
+    try:
+      noise = self._batched_noise([w for _, w in pairs], self.noise_std)
+      self._run_update([self._layer_spec(m, w, self.noise_std, noise=noise.get(w.name)) for m, w in pairs])
+    finally:
+      self._slot_names_cache = None
+
+  def _batched_noise(self, weights, noise_std):
+    if not noise_std:
+      return {}
+    sizes = [(w.numel() + 127) // 128 * 128 for w in weights]
+    total = sum(sizes)
+    flat = getattr(self, '_noise_flat', None)
+    if flat is None or flat.numel() != total or flat.device != weights[0].device:
+      flat = torch.empty(total, dtype=torch.float32, device=weights[0].device)
+      self._noise_flat = flat
+    self._random_normal(flat.shape, stddev=noise_std, dtype=torch.float32, seed=stable_hash('drop'),
+                        out=flat, device=flat.device)
+    views, off = {}, 0
+    for w, sz in zip(weights, sizes):
+      views[w.name] = flat[off:off + w.numel()]
+      off += sz
+    self._noise_bufs = dict(views)
+    return views
 
   def is_mask_update_iter(self, global_step, last_update_step):
     gs = int(global_step)
@@ -281,7 +307,8 @@ class SparseSETOptimizerBase(object):
     return buf
 
   def _slots_of(self, weights):
-    slots = [self.get_slot(weights, n) for n in self.get_slot_names()]
+    names = getattr(self, '_slot_names_cache', None)
+    slots = [self.get_slot(weights, n) for n in (names if names is not None else self.get_slot_names())]
     return [s.view(-1) for s in slots if s is not None]
 
   def _grow_spec(self, weights, method):
@@ -296,12 +323,14 @@ class SparseSETOptimizerBase(object):
     return 0.0
 
   def _layer_spec(self, mask, weights, noise_std, score_drop=None, score_grow=None,
-                  reinit_when_same=False):
+                  reinit_when_same=False, noise=None):
     mode, div, grow_values = self._grow_spec(weights, self._grow_init)
     if score_grow is None:
       score_grow = self._score_grow_for(mask, weights)
+    if noise is None and score_drop is None:
+      noise = self._noise_for(weights, noise_std)
     return dict(mask=mask, weights=weights.data.view(-1), score_grow=score_grow.contiguous().view(-1),
-                noise=None if score_drop is not None else self._noise_for(weights, noise_std),
+                noise=None if score_drop is not None else noise,
                 score_drop=None if score_drop is None else score_drop.contiguous().view(-1),
                 slots=self._slots_of(weights), grow_values=grow_values, grow_mode=mode,
                 grow_divisor=div, reinit_when_same=reinit_when_same)
