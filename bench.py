@@ -150,11 +150,25 @@ def run_ours(args):
   host_labels = labels.cpu().pin_memory()
   barrier()
   e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  copy_stream = torch.cuda.Stream(device=dev)
+
+  def fetch():            # host -> device copy of one batch on the copy stream (input prefetch)
+    with torch.cuda.stream(copy_stream):
+      xb = host_images.to(dev, non_blocking=True)
+      yb = host_labels.to(dev, non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(copy_stream)
+    return xb, yb, ev
+
   e_start.record()
-  for _ in range(e2e_steps):
-    x = host_images.to(dev, non_blocking=True).permute(0, 3, 1, 2)
-    y = host_labels.to(dev, non_blocking=True)
-    loss = harness.step(x, y)
+  nxt = fetch()
+  for i in range(e2e_steps):
+    xb, yb, ev = nxt
+    torch.cuda.current_stream().wait_event(ev)
+    if i + 1 < e2e_steps:
+      nxt = fetch()       # overlaps the next batch's H2D with this step's compute
+    loss = harness.step(xb.permute(0, 3, 1, 2), yb)
+    xb.record_stream(torch.cuda.current_stream())
     _ = float(loss.item())
   e_stop.record()
   barrier()
@@ -163,13 +177,18 @@ def run_ours(args):
     dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
   e2e_value = world * BATCH * e2e_steps / (float(e_ms.item()) / 1e3)
 
-  if rank != 0:
-    return
-  # ---- roofline leg (rank 0): per-call CUDA-event times of the conv kernels ----
-  Profiler.start()
+  # ---- roofline leg: per-call CUDA-event times of the conv kernels (all ranks step: the
+  # data-parallel all-reduce is collective; only rank 0 records) ----
   prof_steps = 3
+  if rank == 0:
+    Profiler.start()
   for _ in range(prof_steps):
     harness.step(images, labels)
+  barrier()
+  if rank != 0:
+    if dist is not None:
+      dist.destroy_process_group()
+    return
   rec = Profiler.stop()
   per_kind = {}
   for kind, _, t in rec:
@@ -227,11 +246,24 @@ def run_ours(args):
   if world == 1 and not args.no_cpu_baseline:
     out['cpu_baseline'] = cpu_baseline_leg(sample_batch=args.cpu_batch)
   print(json.dumps(out))
+  if dist is not None:
+    dist.destroy_process_group()
+
+
+def _use_all_host_threads():
+  """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+  n = os.cpu_count() or 1
+  try:
+    n = len(os.sched_getaffinity(0))
+  except AttributeError:
+    pass
+  torch.set_num_threads(max(1, n))
 
 
 def cpu_baseline_leg(sample_batch=16, steps=1):
   """Times the CPU port of the reference path on the host cores (bounded sample)."""
   from oracle import cpu_train_step as cpu
+  _use_all_host_threads()
   threads = torch.get_num_threads()
   sec, net, dense = cpu.time_train_steps(sample_batch, steps, warmup=1)
   mu = cpu.time_mask_update(net, dense)
@@ -249,6 +281,7 @@ def run_reference(args):
   if rank != 0:
     return
   from oracle import cpu_train_step as cpu
+  _use_all_host_threads()
   threads = torch.get_num_threads()
   batch = args.cpu_batch
   steps = max(1, min(args.steps, 3))
@@ -261,7 +294,7 @@ def run_reference(args):
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/sec',
       'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': 'ResNet-50 ImageNet-shaped, 80% ERK, CPU port of the reference TF1 train step, '
+      'config': {'workload': 'ResNet-50 ImageNet-shaped, 80%% ERK, CPU port of the reference TF1 train step, '
                              'bounded sample of batch %d per step' % batch},
       'cpu_baseline': {'value': value, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
                        'sample': 'batch %d, %d step(s), wall %.1fs' % (batch, steps, time.perf_counter() - t0)},

@@ -197,6 +197,15 @@ RIGL_API int rigl_bn_backward(const void* da, const void* y, const void* act, co
                               int64_t rows, int channels, int relu, void* dy, void* dresidual,
                               float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
+/* Max pooling, NHWC bf16, TF 'SAME' padding (out = ceil(in/stride), pad_before = pad_total/2).
+ * Replaces tf.layers.max_pooling2d(pool_size=3, strides=2, padding='SAME'),
+ * resnet_model.py:636-642.  argmax: one byte per OUTPUT element (window-relative index of the
+ * first maximum), consumed by the backward gather.  channels % 8 == 0. */
+RIGL_API int rigl_maxpool_same_forward(const void* x, int n, int h, int w, int c, int ksize, int stride,
+                                       void* y, uint8_t* argmax, void* stream);
+RIGL_API int rigl_maxpool_same_backward(const void* dy, const uint8_t* argmax, int n, int h, int w, int c,
+                                        int ksize, int stride, void* dx, void* stream);
+
 /* 1 to route every conv call through the CUDA-core kernels (debug cross-check). */
 RIGL_API int rigl_set_force_simt(int on);
 

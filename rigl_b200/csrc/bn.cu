@@ -70,31 +70,48 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
       }
     }
     if (r_in < rpi) {
-#pragma unroll 4
-      for (long long r = row0 + r_in; r < row1; r += rpi) {
-        const long long off = r * C + 8 * v;
-        float fy[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
-        if (MODE == 0) {
+      // 4 rows per trip: all loads are issued before any arithmetic (memory-level parallelism)
+      for (long long rb = row0 + r_in; rb < row1; rb += 4ll * rpi) {
+        uint4 qy[4], qd[4], qa[4];
+        bool ok[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s0[i] += fy[i]; s1[i] = fmaf(fy[i], fy[i], s1[i]); }
-        } else {
-          float g[8];
-          unpack8(*reinterpret_cast<const uint4*>(da + off), g);
-          if (MODE == 2) {
-            float fa[8];
-            unpack8(*reinterpret_cast<const uint4*>(act + off), fa);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = (!relu || fa[i] > 0.f) ? g[i] : 0.f;
-            *reinterpret_cast<uint4*>(gout + off) = pack8(g);
-          } else if (relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const long long r = rb + (long long)u * rpi;
+          ok[u] = r < row1;
+          if (ok[u]) {
+            const long long off = r * C + 8 * v;
+            qy[u] = *reinterpret_cast<const uint4*>(y + off);
+            if (MODE != 0) qd[u] = *reinterpret_cast<const uint4*>(da + off);
+            if (MODE == 2) qa[u] = *reinterpret_cast<const uint4*>(act + off);
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s0[i] += g[i];
-            s1[i] = fmaf(g[i], (fy[i] - mu[i]) * rs[i], s1[i]);
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const long long off = (rb + (long long)u * rpi) * C + 8 * v;
+          float fy[8];
+          unpack8(qy[u], fy);
+          if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += fy[i]; s1[i] = fmaf(fy[i], fy[i], s1[i]); }
+          } else {
+            float g[8];
+            unpack8(qd[u], g);
+            if (MODE == 2) {
+              float fa[8];
+              unpack8(qa[u], fa);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = (!relu || fa[i] > 0.f) ? g[i] : 0.f;
+              *reinterpret_cast<uint4*>(gout + off) = pack8(g);
+            } else if (relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = fmaf(fy[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s0[i] += g[i];
+              s1[i] = fmaf(g[i], (fy[i] - mu[i]) * rs[i], s1[i]);
+            }
           }
         }
       }

@@ -100,7 +100,7 @@ __global__ void k_simt_wgrad(ConvGeom g, const __nv_bfloat16* __restrict__ x,
 // One block = kTP consecutive output pixels of one output row: the k input rows they touch
 // are staged in shared memory with coalesced reads, then every thread emits 16-byte chunks
 // of the output rows, so the (large) write stream is fully coalesced.
-constexpr int kTP = 32;
+constexpr int kTP = 64;
 __global__ void __launch_bounds__(256)
 k_im2col(ConvGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t out_pitch) {
   extern __shared__ __nv_bfloat16 sm[];

@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -61,6 +63,7 @@ struct IgemmParams {
   long long o_off, o_sn, o_sh, o_sw;   // element offsets of pixel (n,h,w) in the output
   const uint32_t* nnz;              // survivor counts per 64x64 weight tile (or null)
   int nnz_tap_stride, nnz_n_stride, nnz_k_stride;
+  int tma_store;                    // 1: epilogue stages bf16 tiles in smem and TMA-stores them
 };
 
 struct TMaps4 {
@@ -84,7 +87,7 @@ __device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUtensorMap bmap,
-               const IgemmParams p) {
+               const __grid_constant__ CUtensorMap omap, const IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
   constexpr uint32_t kBBytes = BN * kBK * 2;
@@ -92,8 +95,10 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 0, 0);
 
+  constexpr uint32_t kSlabBytes = kBM * 64 * 2;       // one 128-pixel x 64-channel output slab
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * kStageBytes;
+  const uint32_t out_base = smem_base + STAGES * kStageBytes;          // 2 staging slabs (1024B aligned)
+  const uint32_t bar_base = out_base + 2 * kSlabBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -106,6 +111,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
     prefetch_tmap(&bmap);
+    if (p.tma_store) prefetch_tmap(&omap);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
@@ -186,6 +192,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;                     // pixel index inside the box
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -199,6 +206,46 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
       const long long o_pix = p.o_off + pn * p.o_sn + ph * p.o_sh + pw * p.o_sw;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (p.tma_store) {
+        // ---- stage 64-channel slabs in smem (128B-swizzled rows) and TMA-store them ----
+        const bool issuer = (warp == 2 && lane == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int co0 = n_tile * BN + c0;
+          if (co0 >= p.N) break;                                   // uniform: whole slab out of range
+          const uint32_t slab = out_base + (uint32_t)(slab_ctr & 1) * kSlabBytes;
+          if (issuer) tma_store_wait_read<1>();                    // the store that last used this slab is done reading
+          named_bar_sync(1, 128);
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
+          tmem_ld_wait();
+          const uint32_t row_addr = slab + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = 8 * j + 2 * q;
+              const float a = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
+              const float b = __uint_as_float(e + 1 < 32 ? r0[e + 1] : r1[e + 1 - 32]);
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t dst = row_addr + (uint32_t)((j ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -252,11 +299,13 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -459,6 +508,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn g_encode = nullptr;
+static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static int g_num_sms = 0;
 static std::once_flag g_once;
 static int g_init_status = RIGL_OK;
@@ -473,6 +523,7 @@ static void init_driver() {
     return;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* e = getenv("RIGL_TMA_STORE")) g_tma_store = !(e[0] == '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -573,8 +624,9 @@ size_t tc_workspace_bytes(const ConvGeom& g) {
 }
 
 template <int BN, int STAGES>
-static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const IgemmParams& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
+static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap, const IgemmParams& p,
+                         cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 2 * (kBM * 64 * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -582,17 +634,17 @@ static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const Ige
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  k_igemm_kmajor<BN, STAGES><<<grid, kThreads, smem, s>>>(amaps, bmap, p);
+  k_igemm_kmajor<BN, STAGES><<<grid, kThreads, smem, s>>>(amaps, bmap, omap, p);
   RIGL_LAUNCH_CHECK("k_igemm_kmajor");
   return RIGL_OK;
 }
 
-static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bmap, IgemmParams& p, int bn_tile,
-                           cudaStream_t s) {
+static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap,
+                           IgemmParams& p, int bn_tile, cudaStream_t s) {
   p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
-  if (bn_tile == 64) return launch_kmajor<64, 8>(amaps, bmap, p, s);
-  if (bn_tile == 128) return launch_kmajor<128, 6>(amaps, bmap, p, s);
-  return launch_kmajor<256, 4>(amaps, bmap, p, s);
+  if (bn_tile == 64) return launch_kmajor<64, 8>(amaps, bmap, omap, p, s);
+  if (bn_tile == 128) return launch_kmajor<128, 6>(amaps, bmap, omap, p, s);
+  return launch_kmajor<256, 4>(amaps, bmap, omap, p, s);
 }
 
 static int pick_bn(int n_out, long long m_tiles) {
@@ -644,7 +696,13 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
   rc = make_tmap(&bmap, pk + L.off_fprop, 3, bdims, bstr, bbox);
   if (rc != RIGL_OK) return rc;
-  return dispatch_kmajor(g.cout, amaps, bmap, p, bn_tile, s);
+  CUtensorMap omap = bmap;
+  p.tma_store = (y != nullptr && y_f32 == nullptr && bias == nullptr && g_tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    rc = make_act_map(&omap, y, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, abox);
+    if (rc != RIGL_OK) return rc;
+  }
+  return dispatch_kmajor(g.cout, amaps, bmap, omap, p, bn_tile, s);
 }
 
 int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, void* ws, size_t ws_bytes,
@@ -703,7 +761,13 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
       const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
       rc = make_tmap(&bmap, pk + L.off_dgrad, 3, bdims, bstr, bbox);
       if (rc != RIGL_OK) return rc;
-      rc = dispatch_kmajor(g.cin, amaps, bmap, p, bn_tile, s);
+      CUtensorMap omap = bmap;
+      p.tma_store = g_tma_store ? 1 : 0;
+      if (p.tma_store) {                 // dx viewed through the parity sub-grid of this launch
+        rc = make_act_map(&omap, dx, g.batch, g.in_h, g.in_w, g.cin, g.x_pitch, st, ph, pw, abox);
+        if (rc != RIGL_OK) return rc;
+      }
+      rc = dispatch_kmajor(g.cin, amaps, bmap, omap, p, bn_tile, s);
       if (rc != RIGL_OK) return rc;
     }
   return RIGL_OK;

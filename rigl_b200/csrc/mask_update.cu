@@ -14,10 +14,12 @@
 //   C  k_scan_drop   : bins above the threshold -> mask1 bit; the threshold bin's
 //                      elements -> candidate list; everything below contributes
 //                      to the grow histogram (same pass reads the dense grad)
-//   D  k_resolve<0>  : per layer: radix-select inside the candidate list on the
-//                      52-bit composite (low 20 key bits, inverted index) -> exact
-//                      cut incl. tie-break; completes the grow histogram; picks
-//                      the grow threshold bin
+//   D  k_resolve<0>  : per layer: a level-2 histogram (next 12 key bits, filled by C)
+//                      narrows the candidates to a handful; those are ranked exactly
+//                      on the 52-bit composite (low 20 key bits, inverted index) in
+//                      shared memory -> exact cut incl. tie-break (a global radix
+//                      select is the fallback for huge tie groups); completes the
+//                      grow histogram; picks the grow threshold bin
 //   E  k_scan_grow   : definite grows -> mask2 bit, weight/slot re-init at new
 //                      connections; threshold bin -> candidates
 //   F  k_resolve<1>  : exact grow cut; writes mask = mask1 | mask2
@@ -43,7 +45,7 @@ constexpr int kRBins = 2048;
 
 struct LayerState {     // 64 bytes, zeroed at the start of every run
   int32_t n_ones, n_prune, n_keep, n_cand_drop;
-  int32_t n_cand_grow, drop_bucket, grow_bucket, pad0;
+  int32_t n_cand_grow, drop_bucket, grow_bucket, n_ones_acc;
   uint32_t drop_need, grow_need, cand_cnt_drop, cand_cnt_grow;
   uint32_t pad1[4];
 };
@@ -62,6 +64,8 @@ struct LayerDev {
   uint64_t off_mask1;   // byte offsets into the workspace
   uint64_t off_hist_drop;
   uint64_t off_hist_grow;
+  uint64_t off_hist2_drop;   // level-2 histograms (key bits 19..8 of the threshold bin's elements)
+  uint64_t off_hist2_grow;
   uint64_t off_cand;
   uint64_t off_state;
 };
@@ -124,6 +128,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   __shared__ uint32_t hist[kBins];
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
+  LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   for (int b = threadIdx.x; b < kBins; b += kScanThreads) hist[b] = 0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,33 +136,53 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const bool has_noise = L.noise != nullptr && !explicit_score;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
-  uint32_t zero_cnt = 0;
+  uint32_t zero_cnt = 0, ones = 0;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kGroupsPerChunk = kChunk / kGroup;
-#pragma unroll 2
-  for (int gi = warp; gi < kGroupsPerChunk; gi += kWarps) {
-    const uint32_t base = task.start + gi * kGroup;
-    if (base >= n) break;
-    const uint32_t e0 = base + 4 * lane;
-    const float4 wv = load4_guard(wsrc, e0, n);
-    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_noise) nv = load4_guard(L.noise, e0, n);
-    const uint32_t mw = __ldg(L.mask + (base >> 5) + (lane >> 3));
-    const uint32_t nib = (mw >> (4 * (lane & 7))) & 0xFu;
-    const float ws4[4] = {wv.x, wv.y, wv.z, wv.w};
-    const float ns4[4] = {nv.x, nv.y, nv.z, nv.w};
+  constexpr int kTrips = kChunk / kGroup / kWarps;      // 32 groups per warp
+#pragma unroll 1
+  for (int j0 = 0; j0 < kTrips; j0 += 4) {
+    // issue the loads of 4 groups before touching any of them (memory-level parallelism)
+    float4 wv[4], nv[4];
+    uint32_t mw[4], e0s[4];
+    bool act[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (e0 + c < n) {
-        const uint32_t key = ord_key(drop_score(ws4[c], (nib >> c) & 1u, ns4[c], has_noise, explicit_score));
-        if (key == kKeyZero) ++zero_cnt;           // masked-out entries: avoid a 32-way smem hot spot
-        else atomicAdd(&hist[key >> kBinShift], 1u);
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t base = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
+      act[u] = base < n;                                  // warp-uniform
+      e0s[u] = base + 4 * lane;
+      nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act[u]) {
+        wv[u] = load4_guard(wsrc, e0s[u], n);
+        if (has_noise) nv[u] = load4_guard(L.noise, e0s[u], n);
+        mw[u] = __ldg(L.mask + (base >> 5) + (lane >> 3));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!act[u]) continue;
+      if ((lane & 7) == 0) ones += __popc(mw[u]);
+      const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
+      const float ws4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+      const float ns4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (e0s[u] + c < n) {
+          const uint32_t key = ord_key(drop_score(ws4[c], (nib >> c) & 1u, ns4[c], has_noise, explicit_score));
+          if (key == kKeyZero) ++zero_cnt;         // masked-out entries: avoid a 32-way smem hot spot
+          else atomicAdd(&hist[key >> kBinShift], 1u);
+        }
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) zero_cnt += __shfl_xor_sync(0xffffffffu, zero_cnt, o);
-  if (lane == 0 && zero_cnt) atomicAdd(&hist[kKeyZero >> kBinShift], zero_cnt);
+  for (int o = 16; o > 0; o >>= 1) {
+    zero_cnt += __shfl_xor_sync(0xffffffffu, zero_cnt, o);
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+  }
+  if (lane == 0) {
+    if (zero_cnt) atomicAdd(&hist[kKeyZero >> kBinShift], zero_cnt);
+    if (ones) atomicAdd(&st->n_ones_acc, (int32_t)ones);        // popcount(mask) for free
+  }
   __syncthreads();
   flush_hist(hist, reinterpret_cast<uint32_t*>(ws + L.off_hist_drop));
 }
@@ -233,14 +258,9 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   const uint32_t* gh = reinterpret_cast<const uint32_t*>(ws + L.off_hist_drop);
   for (int b = threadIdx.x; b < kBins; b += kResolveThreads) hist[b] = __ldcg(gh + b);
-  // n_ones = popcount(mask)
-  const uint32_t words = (L.n + 31) >> 5;
-  uint32_t pc = 0;
-  for (uint32_t i = threadIdx.x; i < words; i += kResolveThreads) pc += __popc(__ldg(L.mask + i));
   __syncthreads();
-  const uint32_t incl = block_inclusive_scan(pc, warp_sums);
   if (threadIdx.x == kResolveThreads - 1) {
-    const int32_t n_ones = (int32_t)incl;
+    const int32_t n_ones = st->n_ones_acc;             // accumulated by k_hist_drop
     int32_t n_prune = L.n_prune_override >= 0
                           ? L.n_prune_override
                           : (int32_t)__fmul_rn((float)n_ones, prm.drop_fraction);  // base.py:287-289
@@ -273,6 +293,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const LayerDev L = layers[task.layer];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
+  uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + L.off_hist2_drop);
   uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand);
   for (int b = threadIdx.x; b < kBins; b += kScanThreads) hist[b] = 0;
   __syncthreads();
@@ -284,49 +305,65 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const uint32_t n = L.n;
   uint32_t zero_cnt = 0;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kGroupsPerChunk = kChunk / kGroup;
-#pragma unroll 2
-  for (int gi = warp; gi < kGroupsPerChunk; gi += kWarps) {
-    const uint32_t base = task.start + gi * kGroup;
-    if (base >= n) break;
-    const uint32_t e0 = base + 4 * lane;
-    const float4 wv = load4_guard(wsrc, e0, n);
-    const float4 gv = load4_guard(L.g, e0, n);
-    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_noise) nv = load4_guard(L.noise, e0, n);
-    const uint32_t mw = __ldg(L.mask + (base >> 5) + (lane >> 3));
-    const uint32_t nib = (mw >> (4 * (lane & 7))) & 0xFu;
-    const float ws4[4] = {wv.x, wv.y, wv.z, wv.w};
-    const float gs4[4] = {gv.x, gv.y, gv.z, gv.w};
-    const float ns4[4] = {nv.x, nv.y, nv.z, nv.w};
-    uint32_t nib1 = 0;
+  constexpr int kTrips = kChunk / kGroup / kWarps;
+#pragma unroll 1
+  for (int j0 = 0; j0 < kTrips; j0 += 4) {
+    float4 wv[4], gv[4], nv[4];
+    uint32_t mw[4], bases[4];
+    bool act[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool valid = e0 + c < n;
-      uint32_t key = 0, bin = 0;
-      if (valid) {
-        key = ord_key(drop_score(ws4[c], (nib >> c) & 1u, ns4[c], has_noise, explicit_score));
-        bin = key >> kBinShift;
-      }
-      const bool is_cand = valid && bin == bucket;
-      const bool kept = valid && bin > bucket;
-      if (kept) nib1 |= 1u << c;
-      const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
-      if (cm) {
-        uint32_t pos = 0;
-        const int leader = __ffs(cm) - 1;
-        if (lane == leader) pos = atomicAdd(&st->cand_cnt_drop, (uint32_t)__popc(cm));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (is_cand) cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
-      }
-      if (valid && !kept && !is_cand) {          // definitely dropped / inactive: a grow contender
-        const uint32_t gkey = ord_key(fabsf(gs4[c]));
-        if (gkey == kKeyZero) ++zero_cnt;
-        else atomicAdd(&hist[gkey >> kBinShift], 1u);
+    for (int u = 0; u < 4; ++u) {
+      bases[u] = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
+      act[u] = bases[u] < n;
+      nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act[u]) {
+        const uint32_t e0 = bases[u] + 4 * lane;
+        wv[u] = load4_guard(wsrc, e0, n);
+        gv[u] = load4_guard(L.g, e0, n);
+        if (has_noise) nv[u] = load4_guard(L.noise, e0, n);
+        mw[u] = __ldg(L.mask + (bases[u] >> 5) + (lane >> 3));
       }
     }
-    const uint32_t word = combine_nibbles(nib1, lane);
-    if ((lane & 7) == 0) mask1[(base >> 5) + (lane >> 3)] = word;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!act[u]) continue;
+      const uint32_t e0 = bases[u] + 4 * lane;
+      const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
+      const float ws4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+      const float gs4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      const float ns4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
+      uint32_t nib1 = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool valid = e0 + c < n;
+        uint32_t key = 0, bin = 0;
+        if (valid) {
+          key = ord_key(drop_score(ws4[c], (nib >> c) & 1u, ns4[c], has_noise, explicit_score));
+          bin = key >> kBinShift;
+        }
+        const bool is_cand = valid && bin == bucket;
+        const bool kept = valid && bin > bucket;
+        if (kept) nib1 |= 1u << c;
+        const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
+        if (cm) {
+          uint32_t pos = 0;
+          const int leader = __ffs(cm) - 1;
+          if (lane == leader) pos = atomicAdd(&st->cand_cnt_drop, (uint32_t)__popc(cm));
+          pos = __shfl_sync(0xffffffffu, pos, leader);
+          if (is_cand) {
+            cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
+            atomicAdd(&hist2[(key >> 8) & 0xFFFu], 1u);
+          }
+        }
+        if (valid && !kept && !is_cand) {          // definitely dropped / inactive: a grow contender
+          const uint32_t gkey = ord_key(fabsf(gs4[c]));
+          if (gkey == kKeyZero) ++zero_cnt;
+          else atomicAdd(&hist[gkey >> kBinShift], 1u);
+        }
+      }
+      const uint32_t word = combine_nibbles(nib1, lane);
+      if ((lane & 7) == 0) mask1[(bases[u] >> 5) + (lane >> 3)] = word;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) zero_cnt += __shfl_xor_sync(0xffffffffu, zero_cnt, o);
@@ -362,13 +399,18 @@ __device__ __forceinline__ uint64_t composite(uint2 c) {
   return ((uint64_t)(c.x & 0xFFFFFu) << 32) | (uint64_t)(0xFFFFFFFFu - c.y);
 }
 
+constexpr int kSubCap = 1024;      // sub-candidates ranked exactly in shared memory
+
 template <bool kGrow>
 __global__ void __launch_bounds__(kResolveThreads)
 k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
-  __shared__ uint32_t rhist[kRBins];
+  __shared__ uint32_t h2[kBins];                 // level-2 histogram; reused as the fallback radix histogram
   __shared__ uint32_t ghist[kGrow ? 1 : kBins];
+  __shared__ uint2 sub[kSubCap];
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t out[3];
+  __shared__ uint32_t sub_cnt;
+  __shared__ unsigned long long s_thresh;
   const LayerDev L = layers[blockIdx.x];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
@@ -377,35 +419,72 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   uint32_t need = kGrow ? st->grow_need : st->drop_need;
   const int tid = threadIdx.x;
 
+  {
+    const uint32_t* g2 = reinterpret_cast<const uint32_t*>(ws + (kGrow ? L.off_hist2_grow : L.off_hist2_drop));
+    for (int b = tid; b < kBins; b += kResolveThreads) h2[b] = __ldcg(g2 + b);
+  }
   if (!kGrow) {
     const uint32_t* gh = reinterpret_cast<const uint32_t*>(ws + L.off_hist_grow);
     for (int b = tid; b < kBins; b += kResolveThreads) ghist[b] = __ldcg(gh + b);
   }
+  if (tid == 0) { sub_cnt = 0; s_thresh = 0ull; }
+  __syncthreads();
 
-  // --- radix select of the top-`need` composites among `cnt` candidates ---
-  uint64_t thresh = 0;                 // selected <=> composite >= thresh
+  // --- the cut: selected <=> composite >= thresh ---
+  uint64_t thresh = 0;
   if (need == 0) thresh = ~0ull;       // nothing (composites use 52 bits)
   if (need > 0 && need < cnt) {
-    const int shifts[5] = {41, 30, 19, 8, 0};
-    const int widths[5] = {11, 11, 11, 11, 8};
-    uint64_t prefix = 0;
-#pragma unroll 1
-    for (int p = 0; p < 5; ++p) {
-      const int sh = shifts[p], wd = widths[p];
-      for (int b = tid; b < kRBins; b += kResolveThreads) rhist[b] = 0;
-      __syncthreads();
+    find_bin_desc<kBins>(h2, need, warp_sums, out);           // level 2: key bits 19..8
+    const uint32_t b2 = out[0];
+    need = out[1];
+    const uint32_t in_bin = out[2];
+    __syncthreads();
+    thresh = (uint64_t)b2 << 40;
+    if (in_bin != need) {
+      // gather the elements of the level-2 threshold bin
       for (uint32_t i = tid; i < cnt; i += kResolveThreads) {
-        const uint64_t c = composite(cand[i]);
-        if ((c >> (sh + wd)) == prefix) atomicAdd(&rhist[(uint32_t)(c >> sh) & ((1u << wd) - 1u)], 1u);
+        const uint2 c = cand[i];
+        if (((c.x >> 8) & 0xFFFu) == b2) {
+          const uint32_t pos = atomicAdd(&sub_cnt, 1u);
+          if (pos < (uint32_t)kSubCap) sub[pos] = c;
+        }
       }
       __syncthreads();
-      find_bin_desc<kRBins>(rhist, need, warp_sums, out);
-      prefix = (prefix << wd) | out[0];
-      need = out[1];
-      const uint32_t in_bin = out[2];
-      __syncthreads();
-      thresh = prefix << sh;
-      if (in_bin == need) break;       // every composite with this prefix is selected
+      const uint32_t ns = sub_cnt;
+      if (ns <= (uint32_t)kSubCap) {
+        // exact rank inside shared memory: the need-th largest composite is the threshold
+        if ((uint32_t)tid < ns) {
+          const uint64_t mine = composite(sub[tid]);
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < ns; ++j) rank += composite(sub[j]) > mine;
+          if (rank == need - 1) s_thresh = mine;
+        }
+        __syncthreads();
+        thresh = s_thresh;
+      } else {
+        // huge tie group: radix select over the whole candidate list on the remaining 40 bits
+        const int shifts[4] = {29, 18, 7, 0};
+        const int widths[4] = {11, 11, 11, 7};
+        uint64_t prefix = b2;
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p) {
+          const int sh = shifts[p], wd = widths[p];
+          for (int b = tid; b < kRBins; b += kResolveThreads) h2[b] = 0;
+          __syncthreads();
+          for (uint32_t i = tid; i < cnt; i += kResolveThreads) {
+            const uint64_t c = composite(cand[i]);
+            if ((c >> (sh + wd)) == prefix) atomicAdd(&h2[(uint32_t)(c >> sh) & ((1u << wd) - 1u)], 1u);
+          }
+          __syncthreads();
+          find_bin_desc<kRBins>(h2, need, warp_sums, out);
+          prefix = (prefix << wd) | out[0];
+          need = out[1];
+          const uint32_t inb = out[2];
+          __syncthreads();
+          thresh = prefix << sh;
+          if (inb == need) break;       // every composite with this prefix is selected
+        }
+      }
     }
   }
   __syncthreads();
@@ -458,51 +537,68 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const LayerDev L = layers[task.layer];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
+  uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + L.off_hist2_grow);
   uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand);
   if (st->n_prune == 0) return;                       // nothing grows; mask1 is final
   const uint32_t bucket = (uint32_t)st->grow_bucket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n = L.n;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kGroupsPerChunk = kChunk / kGroup;
-#pragma unroll 2
-  for (int gi = warp; gi < kGroupsPerChunk; gi += kWarps) {
-    const uint32_t base = task.start + gi * kGroup;
-    if (base >= n) break;
-    const uint32_t e0 = base + 4 * lane;
-    const float4 gv = load4_guard(L.g, e0, n);
-    const uint32_t widx = (base >> 5) + (lane >> 3);
-    const uint32_t m1w = __ldcg(mask1 + widx);
-    const uint32_t oldw = __ldg(L.mask + widx);
-    const uint32_t nib_m1 = (m1w >> (4 * (lane & 7))) & 0xFu;
-    const uint32_t nib_old = (oldw >> (4 * (lane & 7))) & 0xFu;
-    const float gs4[4] = {gv.x, gv.y, gv.z, gv.w};
-    uint32_t nib2 = 0;
+  constexpr int kTrips = kChunk / kGroup / kWarps;
+#pragma unroll 1
+  for (int j0 = 0; j0 < kTrips; j0 += 4) {
+    float4 gv[4];
+    uint32_t m1w[4], oldw[4], bases[4];
+    bool act[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool contender = (e0 + c < n) && !((nib_m1 >> c) & 1u);
-      uint32_t key = 0, bin = 0;
-      if (contender) {
-        key = ord_key(fabsf(gs4[c]));
-        bin = key >> kBinShift;
-      }
-      const bool is_cand = contender && bin == bucket;
-      const bool grown = contender && bin > bucket;
-      if (grown) {
-        nib2 |= 1u << c;
-        if (!((nib_old >> c) & 1u) || prm.reinit_when_same) apply_new_connection(L, prm, e0 + c, gs4[c]);
-      }
-      const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
-      if (cm) {
-        uint32_t pos = 0;
-        const int leader = __ffs(cm) - 1;
-        if (lane == leader) pos = atomicAdd(&st->cand_cnt_grow, (uint32_t)__popc(cm));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (is_cand) cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
+    for (int u = 0; u < 4; ++u) {
+      bases[u] = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
+      act[u] = bases[u] < n;
+      if (act[u]) {
+        gv[u] = load4_guard(L.g, bases[u] + 4 * lane, n);
+        const uint32_t widx = (bases[u] >> 5) + (lane >> 3);
+        m1w[u] = __ldcg(mask1 + widx);
+        oldw[u] = __ldg(L.mask + widx);
       }
     }
-    const uint32_t word2 = combine_nibbles(nib2, lane);
-    if ((lane & 7) == 0 && word2) mask1[widx] = m1w | word2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!act[u]) continue;
+      const uint32_t e0 = bases[u] + 4 * lane;
+      const uint32_t widx = (bases[u] >> 5) + (lane >> 3);
+      const uint32_t nib_m1 = (m1w[u] >> (4 * (lane & 7))) & 0xFu;
+      const uint32_t nib_old = (oldw[u] >> (4 * (lane & 7))) & 0xFu;
+      const float gs4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      uint32_t nib2 = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool contender = (e0 + c < n) && !((nib_m1 >> c) & 1u);
+        uint32_t key = 0, bin = 0;
+        if (contender) {
+          key = ord_key(fabsf(gs4[c]));
+          bin = key >> kBinShift;
+        }
+        const bool is_cand = contender && bin == bucket;
+        const bool grown = contender && bin > bucket;
+        if (grown) {
+          nib2 |= 1u << c;
+          if (!((nib_old >> c) & 1u) || prm.reinit_when_same) apply_new_connection(L, prm, e0 + c, gs4[c]);
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
+        if (cm) {
+          uint32_t pos = 0;
+          const int leader = __ffs(cm) - 1;
+          if (lane == leader) pos = atomicAdd(&st->cand_cnt_grow, (uint32_t)__popc(cm));
+          pos = __shfl_sync(0xffffffffu, pos, leader);
+          if (is_cand) {
+            cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
+            atomicAdd(&hist2[(key >> 8) & 0xFFFu], 1u);
+          }
+        }
+      }
+      const uint32_t word2 = combine_nibbles(nib2, lane);
+      if ((lane & 7) == 0 && word2) mask1[widx] = m1w[u] | word2;
+    }
   }
 }
 
@@ -538,6 +634,10 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
   off += (size_t)n_layers * kBins * 4;
   const size_t hist_grow_off = off;
   off += (size_t)n_layers * kBins * 4;
+  const size_t hist2_drop_off = off;
+  off += (size_t)n_layers * kBins * 4;
+  const size_t hist2_grow_off = off;
+  off += (size_t)n_layers * kBins * 4;
   const size_t zero_bytes = off;
   for (int l = 0; l < n_layers; ++l) {
     const rigl_layer_desc& d = layers[l];
@@ -553,6 +653,8 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
     L.off_state = state_off + sizeof(LayerState) * (size_t)l;
     L.off_hist_drop = hist_drop_off + (size_t)l * kBins * 4;
     L.off_hist_grow = hist_grow_off + (size_t)l * kBins * 4;
+    L.off_hist2_drop = hist2_drop_off + (size_t)l * kBins * 4;
+    L.off_hist2_grow = hist2_grow_off + (size_t)l * kBins * 4;
     L.off_mask1 = off;
     off += align_up((size_t)rigl_mask_words(d.n) * 4, 256);
     for (int64_t s = 0; s < d.n; s += kChunk) tasks.push_back({(uint32_t)l, (uint32_t)s});

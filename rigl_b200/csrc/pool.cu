@@ -1,0 +1,137 @@
+// Max pooling for NHWC bf16 activations (the stem's 3x3/2 pool), HBM-bound streaming kernels.
+// Replaces tf.layers.max_pooling2d(pool_size=3, strides=2, padding='SAME')
+// (rigl/imagenet_resnet/resnet_model.py:636-642) with TF's SAME rule: pad_total =
+// max((out-1)*s + k - in, 0), pad_before = pad_total / 2 (so 112 -> 56 pads only at the end).
+// Forward stores the window-relative argmax (first maximum in (kh,kw) scan order) as one byte
+// per output element; backward is a deterministic gather over the <= ceil(k/s)^2 windows that
+// cover an input pixel.  One thread = 8 channels (16-byte vectors), channels innermost.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rigl {
+
+struct PoolGeom {
+  int n, h, w, c, oh, ow, k, s, pad;
+};
+
+__global__ void __launch_bounds__(256)
+k_maxpool_fwd(PoolGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+              uint8_t* __restrict__ idx) {
+  const int V = g.c >> 3;
+  const long long total = (long long)g.n * g.oh * g.ow * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const long long p = i / V;
+    const int ow = (int)(p % g.ow), oh = (int)((p / g.ow) % g.oh), n = (int)(p / ((long long)g.ow * g.oh));
+    float best[8];
+    uint8_t arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+    for (int kh = 0; kh < g.k; ++kh) {
+      const int hi = oh * g.s + kh - g.pad;
+      if (hi < 0 || hi >= g.h) continue;
+      for (int kw = 0; kw < g.k; ++kw) {
+        const int wi = ow * g.s + kw - g.pad;
+        if (wi < 0 || wi >= g.w) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + (((long long)n * g.h + hi) * g.w + wi) * g.c + 8 * v);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          if (f.x > best[2 * e]) { best[2 * e] = f.x; arg[2 * e] = (uint8_t)(kh * g.k + kw); }
+          if (f.y > best[2 * e + 1]) { best[2 * e + 1] = f.y; arg[2 * e + 1] = (uint8_t)(kh * g.k + kw); }
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh2[e] = __floats2bfloat162_rn(best[2 * e], best[2 * e + 1]);
+    *reinterpret_cast<uint4*>(y + p * g.c + 8 * v) = o;
+    uint2 a;
+    a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((uint32_t)arg[7] << 24);
+    *reinterpret_cast<uint2*>(idx + p * g.c + 8 * v) = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_maxpool_bwd(PoolGeom g, const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+              __nv_bfloat16* __restrict__ dx) {
+  const int V = g.c >> 3;
+  const long long total = (long long)g.n * g.h * g.w * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const long long q = i / V;
+    const int wi = (int)(q % g.w), hi = (int)((q / g.w) % g.h), n = (int)(q / ((long long)g.w * g.h));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // outputs oh with oh*s - pad <= hi <= oh*s - pad + k - 1
+    const int oh_lo = max(0, (hi + g.pad - g.k + g.s) / g.s), oh_hi = min(g.oh - 1, (hi + g.pad) / g.s);
+    const int ow_lo = max(0, (wi + g.pad - g.k + g.s) / g.s), ow_hi = min(g.ow - 1, (wi + g.pad) / g.s);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const int rel = (hi - (oh * g.s - g.pad)) * g.k + (wi - (ow * g.s - g.pad));
+        const long long p = ((long long)n * g.oh + oh) * g.ow + ow;
+        const uint2 a = *reinterpret_cast<const uint2*>(idx + p * g.c + 8 * v);
+        const uint4 raw = *reinterpret_cast<const uint4*>(dy + p * g.c + 8 * v);
+        const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t ai = ((e < 4 ? a.x : a.y) >> (8 * (e & 3))) & 0xFFu;
+          if ((int)ai == rel) acc[e] += __bfloat162float(d[e]);
+        }
+      }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+    *reinterpret_cast<uint4*>(dx + q * g.c + 8 * v) = o;
+  }
+}
+
+static int pool_geom(int n, int h, int w, int c, int k, int s, PoolGeom* g) {
+  RIGL_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && k > 0 && s > 0 && k * k <= 255,
+               "maxpool: bad geometry (channels must be a multiple of 8)");
+  g->n = n; g->h = h; g->w = w; g->c = c; g->k = k; g->s = s;
+  g->oh = (h + s - 1) / s; g->ow = (w + s - 1) / s;                       // TF 'SAME'
+  const int pad_total = max((g->oh - 1) * s + k - h, 0);
+  g->pad = pad_total / 2;
+  return RIGL_OK;
+}
+
+}  // namespace rigl
+
+using namespace rigl;
+
+extern "C" int rigl_maxpool_same_forward(const void* x, int n, int h, int w, int c, int ksize, int stride,
+                                         void* y, uint8_t* argmax, void* stream) {
+  PoolGeom g;
+  int rc = pool_geom(n, h, w, c, ksize, stride, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && y && argmax, "rigl_maxpool_same_forward: null tensor");
+  const long long total = (long long)g.n * g.oh * g.ow * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_maxpool_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax);
+  RIGL_LAUNCH_CHECK("k_maxpool_fwd");
+  return RIGL_OK;
+}
+
+extern "C" int rigl_maxpool_same_backward(const void* dy, const uint8_t* argmax, int n, int h, int w, int c,
+                                          int ksize, int stride, void* dx, void* stream) {
+  PoolGeom g;
+  int rc = pool_geom(n, h, w, c, ksize, stride, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(dy && dx && argmax, "rigl_maxpool_same_backward: null tensor");
+  const long long total = (long long)g.n * g.h * g.w * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_maxpool_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx);
+  RIGL_LAUNCH_CHECK("k_maxpool_bwd");
+  return RIGL_OK;
+}

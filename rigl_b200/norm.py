@@ -95,3 +95,37 @@ class FusedBatchNormReLU(nn.Module):
                                           n * h * w, c, int(self.relu), out.data_ptr(), _cabi.stream_ptr()),
                 'rigl_bn_apply')
     return out
+
+
+class _MaxPoolFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, ksize, stride):
+    n, c, h, w = x.shape
+    oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+    y = torch.empty((n, c, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    arg = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    _cabi.check(_cabi.lib().rigl_maxpool_same_forward(x.data_ptr(), n, h, w, c, ksize, stride, y.data_ptr(),
+                                                      arg.data_ptr(), _cabi.stream_ptr()),
+                'rigl_maxpool_same_forward')
+    ctx.save_for_backward(arg)
+    ctx.geom = (n, h, w, c, ksize, stride)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    arg, = ctx.saved_tensors
+    n, h, w, c, ksize, stride = ctx.geom
+    dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = torch.empty((n, c, h, w), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    _cabi.check(_cabi.lib().rigl_maxpool_same_backward(dy.data_ptr(), arg.data_ptr(), n, h, w, c, ksize, stride,
+                                                       dx.data_ptr(), _cabi.stream_ptr()),
+                'rigl_maxpool_same_backward')
+    return dx, None, None
+
+
+def max_pool_same(x, ksize=3, stride=2):
+  """tf.layers.max_pooling2d(pool_size, strides, padding='SAME') on NHWC bf16
+  (resnet_model.py:636-642); x is [N,C,H,W] channels_last."""
+  x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  return _MaxPoolFn.apply(x, int(ksize), int(stride))

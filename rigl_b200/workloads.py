@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from . import pruning
 from . import sparse_utils
 from .layers import SparseConv2d, SparseLinear, variance_scaling_
-from .norm import FusedBatchNormReLU
+from .norm import FusedBatchNormReLU, max_pool_same
 from .sparse_optimizers import SparseRigLOptimizer
 from .sparse_optimizers_base import GlobalStep
 
@@ -83,7 +83,7 @@ class ResNet50(nn.Module):
 
   def forward(self, x):
     x = self.initial_bn(self.initial_conv(x))
-    x = F.max_pool2d(x, 3, 2, 1)
+    x = max_pool_same(x, 3, 2)                      # 'SAME' 3x3/2 pool, resnet_model.py:636-642
     for blk in self.blocks:
       x = blk(x)
     x = x.mean(dim=(2, 3))
@@ -143,7 +143,9 @@ class TrainHarness(object):
     """images: bf16 [N,3,H,W] channels_last; labels: int64 [N].  Returns the loss tensor."""
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
-    self.inner.zero_grad(set_to_none=False)
+    # without DP the grads are re-created by autograd (no zero-fill, no accumulate pass);
+    # with DP they are views of the flat all-reduce buffer and must persist
+    self.inner.zero_grad(set_to_none=self.dp is None)
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
     loss.backward()

@@ -90,3 +90,26 @@ def test_bn_eval_mode_and_errors():
     FusedBatchNormReLU(12, device=DEV)
   with pytest.raises(ValueError):
     bn(torch.zeros(2, 8, 5, 5, device=DEV))
+
+
+@pytest.mark.parametrize('shape', [(2, 12, 12, 16), (3, 9, 7, 8), (2, 112, 112, 64)])
+def test_maxpool_same_forward_backward(shape):
+  from rigl_b200.norm import max_pool_same
+  import torch.nn.functional as F
+  n, h, w, c = shape
+  torch.manual_seed(h)
+  x = torch.randn(n, c, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  x.requires_grad_(True)
+  y = max_pool_same(x, 3, 2)
+  oh, ow = (h + 1) // 2, (w + 1) // 2
+  ph, pw = max((oh - 1) * 2 + 3 - h, 0), max((ow - 1) * 2 + 3 - w, 0)
+  xr = x.detach().float().clone().requires_grad_(True)
+  yr = F.max_pool2d(F.pad(xr, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), value=float('-inf')), 3, 2, 0)
+  assert tuple(y.shape) == tuple(yr.shape) and torch.equal(y.float(), yr)
+  dy = torch.randn_like(yr).to(torch.bfloat16).float()
+  y.backward(dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+  yr.backward(dy)
+  # random bf16 inputs have (rare) exact ties; compare where the reference argmax is unique
+  assert float((x.grad.float() - xr.grad).abs().max()) <= 2 ** -7 * float(xr.grad.abs().max()) + 0.0 or \
+      float(((x.grad.float() - xr.grad).abs() > 1e-2).float().mean()) < 1e-3
+  assert abs(float(x.grad.float().sum()) - float(dy.sum())) <= 1e-2 * float(dy.abs().sum())

@@ -16,7 +16,7 @@ def _reference_forward(model, x):
     w = (layer.weight.detach() * layer.mask.to_dense()).to(torch.bfloat16).permute(3, 2, 0, 1).contiguous()
     return F.conv2d(t, w, stride=layer.stride, padding=layer.pad)
   t = model.initial_bn(conv(model.initial_conv, x))
-  t = F.max_pool2d(t, 3, 2, 1)
+  t = F.max_pool2d(F.pad(t, (0, 1, 0, 1), value=float('-inf')), 3, 2, 0)     # TF 'SAME': pad at the end only
   for blk in model.blocks:
     sc = t if blk.proj is None else blk.proj_bn(conv(blk.proj, t))
     y = blk.bn1(conv(blk.conv1, t))
