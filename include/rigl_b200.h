@@ -148,7 +148,9 @@ RIGL_API int rigl_pack_masked_weights(const float* w_hwio, const uint32_t* mask_
 typedef struct {
   int32_t batch, in_h, in_w, cin;     /* x  [batch,in_h,in_w,cin]   bf16 NHWC */
   int32_t out_h, out_w, cout;         /* y  [batch,out_h,out_w,cout] bf16 NHWC */
-  int32_t ksize, stride, pad;         /* square; pad = (ksize-1)/2 (resnet_model.py:83-108,278-281) */
+  int32_t ksize, stride, pad;         /* square; pad = zero rows/cols BEFORE the image: (k-1)/2 for
+                                         conv2d_fixed_padding (resnet_model.py:83-108,278-281), TF 'SAME'
+                                         pad_total/2, 0 for 'VALID'; the far edge is padded implicitly */
   int32_t x_pitch;                    /* elements between consecutive pixels of x (0 => cin); lets a
                                          zero-padded buffer (e.g. the im2col matrix) be addressed */
 } rigl_conv_desc;

@@ -363,6 +363,51 @@ def masked_linear_bwd(x, w_io, mask_io, dy):
   return dx, dw_dense, dw_dense * mask_io
 
 
+def tf_same_padding(size, k, stride):
+  """TensorFlow 'SAME': (output extent, pad_before, pad_after)."""
+  out = -(-size // stride)
+  total = max((out - 1) * stride + k - size, 0)
+  return out, total // 2, total - total // 2
+
+
+def conv2d_nhwc_general(x, w_hwio, stride, pad_before, out_hw):
+  """float64 NHWC conv with `pad_before` zeros before the image and as many after as the
+  requested output size needs (covers TF 'SAME' stride-2 asymmetry)."""
+  n, h, w, c = x.shape
+  kh, kw, ci, co = w_hwio.shape
+  ho, wo = out_hw
+  ph = max((ho - 1) * stride + kh - h - pad_before, 0)
+  pw = max((wo - 1) * stride + kw - w - pad_before, 0)
+  xp = np.zeros((n, h + pad_before + ph, w + pad_before + pw, c), np.float64)
+  xp[:, pad_before:pad_before + h, pad_before:pad_before + w, :] = x
+  y = np.zeros((n, ho, wo, co), np.float64)
+  for i in range(kh):
+    for j in range(kw):
+      patch = xp[:, i:i + stride * (ho - 1) + 1:stride, j:j + stride * (wo - 1) + 1:stride, :]
+      y += patch.reshape(-1, c).dot(w_hwio[i, j].astype(np.float64)).reshape(n, ho, wo, co)
+  return y
+
+
+def conv2d_nhwc_general_bwd(x, w_hwio, dy, stride, pad_before):
+  n, h, w, c = x.shape
+  kh, kw, ci, co = w_hwio.shape
+  ho, wo = dy.shape[1:3]
+  ph = max((ho - 1) * stride + kh - h - pad_before, 0)
+  pw = max((wo - 1) * stride + kw - w - pad_before, 0)
+  xp = np.zeros((n, h + pad_before + ph, w + pad_before + pw, c), np.float64)
+  xp[:, pad_before:pad_before + h, pad_before:pad_before + w, :] = x
+  dxp = np.zeros_like(xp)
+  dw = np.zeros(w_hwio.shape, np.float64)
+  dyf = dy.reshape(-1, co).astype(np.float64)
+  for i in range(kh):
+    for j in range(kw):
+      sl = (slice(None), slice(i, i + stride * (ho - 1) + 1, stride),
+            slice(j, j + stride * (wo - 1) + 1, stride), slice(None))
+      dw[i, j] = xp[sl].reshape(-1, c).T.dot(dyf)
+      dxp[sl] += dyf.dot(w_hwio[i, j].astype(np.float64).T).reshape(n, ho, wo, c)
+  return dxp[:, pad_before:pad_before + h, pad_before:pad_before + w, :], dw
+
+
 def conv2d_nhwc_fwd(x, w_hwio, stride, pad):
   """Plain-loop-free float64 NHWC conv, symmetric zero pad `pad`, square stride.
 

@@ -204,20 +204,27 @@ k_bn_finalize_bwd(const float* __restrict__ partial, int nblocks, int C, long lo
   coef[C + c] = (float)(sc * (r * m * c1 - c0));
 }
 
-// a = [relu](y*scale + shift (+ residual))
+__device__ __forceinline__ void load8f(const float* __restrict__ p, int v, float (&o)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[2 * v], b = reinterpret_cast<const float4*>(p)[2 * v + 1];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// a = [relu](y*scale + shift (+ residual)).  The grid stride is a multiple of V whenever V
+// divides the thread count, so each thread keeps ONE channel vector: its coefficients are
+// loaded once and the loop only streams activations.
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
            const float* __restrict__ scale, const float* __restrict__ shift, int relu, long long nvec, int V,
            __nv_bfloat16* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % V);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fixed_v = (stride % V) == 0;
+  float sc[8], sh[8];
+  if (fixed_v) { load8f(scale, (int)(i0 % V), sc); load8f(shift, (int)(i0 % V), sh); }
+  for (long long i = i0; i < nvec; i += stride) {
+    if (!fixed_v) { load8f(scale, (int)(i % V), sc); load8f(shift, (int)(i % V), sh); }
     float f[8];
     unpack8(reinterpret_cast<const uint4*>(y)[i], f);
-    const float4 s0 = reinterpret_cast<const float4*>(scale)[2 * v], s1 = reinterpret_cast<const float4*>(scale)[2 * v + 1];
-    const float4 b0 = reinterpret_cast<const float4*>(shift)[2 * v], b1 = reinterpret_cast<const float4*>(shift)[2 * v + 1];
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
     if (residual) {
@@ -234,28 +241,28 @@ k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
   }
 }
 
-__device__ __forceinline__ void load8f(const float* __restrict__ p, int v, float (&o)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(p)[2 * v], b = reinterpret_cast<const float4*>(p)[2 * v + 1];
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-}
-
 // dy = scale*g + P*y + Q;  g = da * relu' (recomputed from y) or the stored g.
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_bwd_apply(const __nv_bfloat16* __restrict__ g_or_da, const __nv_bfloat16* __restrict__ y,
                const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
                int relu_recompute, long long nvec, int V, int C, __nv_bfloat16* __restrict__ dy) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % V);
-    float g[8], fy[8], o[8], sc[8], P[8], Q[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fixed_v = (stride % V) == 0;
+  float sc[8], sh[8], P[8], Q[8];
+  if (fixed_v) {
+    const int v = (int)(i0 % V);
+    load8f(scale, v, sc); load8f(shift, v, sh); load8f(coef, v, P); load8f(coef + C, v, Q);
+  }
+  for (long long i = i0; i < nvec; i += stride) {
+    if (!fixed_v) {
+      const int v = (int)(i % V);
+      load8f(scale, v, sc); load8f(shift, v, sh); load8f(coef, v, P); load8f(coef + C, v, Q);
+    }
+    float g[8], fy[8], o[8];
     unpack8(reinterpret_cast<const uint4*>(g_or_da)[i], g);
     unpack8(reinterpret_cast<const uint4*>(y)[i], fy);
-    load8f(scale, v, sc);
-    load8f(coef, v, P);
-    load8f(coef + C, v, Q);
     if (relu_recompute) {
-      float sh[8];
-      load8f(shift, v, sh);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (!(fmaf(fy[k], sc[k], sh[k]) > 0.f)) g[k] = 0.f;

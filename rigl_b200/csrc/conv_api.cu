@@ -23,10 +23,13 @@ int geom_from_desc(const rigl_conv_desc* d, ConvGeom* g) {
   RIGL_REQUIRE(d->batch > 0 && d->in_h > 0 && d->in_w > 0 && d->cin > 0 && d->cout > 0 && d->ksize > 0 &&
                    d->stride > 0 && d->pad >= 0,
                "conv desc: non-positive dimension");
-  const int eh = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
-  const int ew = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
-  RIGL_REQUIRE(d->out_h == eh && d->out_w == ew, "conv desc: out %dx%d inconsistent (expected %dx%d)",
-               d->out_h, d->out_w, eh, ew);
+  // `pad` is the padding BEFORE the image; windows may overrun the far edge (implicit zero
+  // padding there), which covers TF 'SAME' (asymmetric for stride 2), explicit fixed padding
+  // and 'VALID'.  Every window must start inside the padded image.
+  RIGL_REQUIRE(d->pad < d->ksize && d->out_h > 0 && d->out_w > 0 &&
+                   (d->out_h - 1) * d->stride - d->pad < d->in_h && (d->out_w - 1) * d->stride - d->pad < d->in_w,
+               "conv desc: output %dx%d inconsistent with input %dx%d, k=%d, stride=%d, pad=%d", d->out_h,
+               d->out_w, d->in_h, d->in_w, d->ksize, d->stride, d->pad);
   g->batch = d->batch; g->in_h = d->in_h; g->in_w = d->in_w; g->cin = d->cin;
   g->out_h = d->out_h; g->out_w = d->out_w; g->cout = d->cout;
   g->ksize = d->ksize; g->stride = d->stride; g->pad = d->pad;

@@ -123,23 +123,26 @@ k_im2col(ConvGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
       v = x[(((int64_t)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch + c];
     sm[idx] = v;
   }
-  __syncthreads();
+  // source offset (inside the staged rows, for pixel 0) of every output column: no divisions
+  // in the streaming loop
   const int kc = g.ksize * g.cin;                 // elements per kh segment
   const int K = g.ksize * kc;
+  int* src_off = reinterpret_cast<int*>(sm + ((g.ksize * rowlen + 7) & ~7));
+  for (int kk = threadIdx.x; kk < (int)out_pitch; kk += blockDim.x) {
+    const int kh = kk / kc;
+    src_off[kk] = kk < K ? kh * rowlen + (kk - kh * kc) : -1;
+  }
+  __syncthreads();
   const int cpr = (int)(out_pitch / 8);           // 16-byte chunks per output row
+  const int pstep = g.stride * g.cin;
   const int64_t p0 = ((int64_t)n * g.out_h + ho) * g.out_w + wo0;
   for (int q = threadIdx.x; q < npix * cpr; q += blockDim.x) {
     const int pl = q / cpr, j = q - pl * cpr;
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int kk = 8 * j + e;
-      __nv_bfloat16 t = zero;
-      if (kk < K) {
-        const int kh = kk / kc, r = kk - kh * kc;
-        t = sm[kh * rowlen + pl * g.stride * g.cin + r];
-      }
-      v[e] = t;
+      const int so = src_off[8 * j + e];
+      v[e] = so >= 0 ? sm[so + pl * pstep] : zero;
     }
     *reinterpret_cast<uint4*>(out + (p0 + pl) * out_pitch + 8 * j) = *reinterpret_cast<const uint4*>(v);
   }
@@ -149,7 +152,8 @@ int simt_im2col(const ConvGeom& g, const void* x, void* out, int64_t out_pitch, 
   RIGL_REQUIRE(out_pitch % 8 == 0 && aligned16(out), "rigl_im2col_nhwc: out_pitch must be a multiple of 8");
   const int segs = (g.out_w + kTP - 1) / kTP;
   const int span = (kTP - 1) * g.stride + g.ksize;
-  const size_t smem = (size_t)g.ksize * span * g.cin * sizeof(__nv_bfloat16);
+  const size_t smem = (((size_t)g.ksize * span * g.cin + 7) & ~(size_t)7) * sizeof(__nv_bfloat16) +
+                      (size_t)out_pitch * sizeof(int);
   RIGL_REQUIRE(smem <= 48 * 1024, "rigl_im2col_nhwc: patch rows too large for shared memory (%zu B)", smem);
   const int64_t blocks = (int64_t)g.batch * g.out_h * segs;
   k_im2col<<<(unsigned)blocks, 256, smem, s>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, out_pitch);

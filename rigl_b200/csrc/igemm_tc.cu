@@ -594,7 +594,6 @@ bool tc_supported(const ConvGeom& g, int which) {
   if (which == 1 && g.cin % 8) return false;         // dgrad stores 8 channels at a time
   if (g.stride != 1 && g.stride != 2) return false;
   if (g.ksize * g.ksize > kMaxTaps) return false;
-  if (g.pad != (g.ksize - 1) / 2 && !(g.pad == 0 && g.ksize == 1)) return false;
   (void)which;
   return true;
 }

@@ -42,6 +42,7 @@ constexpr int kGroup = 128;                 // elements per warp-iteration (floa
 constexpr int kChunk = 32768;               // elements per block
 constexpr int kResolveThreads = 1024;
 constexpr int kRBins = 2048;
+constexpr int kBatch = 2;                   // groups whose loads are issued together per trip
 
 struct LayerState {     // 64 bytes, zeroed at the start of every run
   int32_t n_ones, n_prune, n_keep, n_cand_drop;
@@ -123,7 +124,7 @@ __device__ __forceinline__ void flush_hist(const uint32_t* sh, uint32_t* gh) {
 // ----------------------------------------------------------------------------
 // A: histogram of drop keys
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws) {
   __shared__ uint32_t hist[kBins];
   const BlockTask task = tasks[blockIdx.x];
@@ -140,13 +141,13 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;      // 32 groups per warp
 #pragma unroll 1
-  for (int j0 = 0; j0 < kTrips; j0 += 4) {
+  for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
     // issue the loads of 4 groups before touching any of them (memory-level parallelism)
-    float4 wv[4], nv[4];
-    uint32_t mw[4], e0s[4];
-    bool act[4];
+    float4 wv[kBatch], nv[kBatch];
+    uint32_t mw[kBatch], e0s[kBatch];
+    bool act[kBatch];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       const uint32_t base = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
       act[u] = base < n;                                  // warp-uniform
       e0s[u] = base + 4 * lane;
@@ -158,7 +159,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       if (!act[u]) continue;
       if ((lane & 7) == 0) ones += __popc(mw[u]);
       const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
@@ -286,7 +287,7 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
 // ----------------------------------------------------------------------------
 // C: classify against the drop threshold bin, build mask1, grow histogram
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws) {
   __shared__ uint32_t hist[kBins];
   const BlockTask task = tasks[blockIdx.x];
@@ -307,12 +308,12 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;
 #pragma unroll 1
-  for (int j0 = 0; j0 < kTrips; j0 += 4) {
-    float4 wv[4], gv[4], nv[4];
-    uint32_t mw[4], bases[4];
-    bool act[4];
+  for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
+    float4 wv[kBatch], gv[kBatch], nv[kBatch];
+    uint32_t mw[kBatch], bases[kBatch];
+    bool act[kBatch];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       bases[u] = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
       act[u] = bases[u] < n;
       nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -325,7 +326,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       if (!act[u]) continue;
       const uint32_t e0 = bases[u] + 4 * lane;
       const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
@@ -530,7 +531,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
 // ----------------------------------------------------------------------------
 // E: classify against the grow threshold bin
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws,
             RunParams prm) {
   const BlockTask task = tasks[blockIdx.x];
@@ -546,12 +547,12 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;
 #pragma unroll 1
-  for (int j0 = 0; j0 < kTrips; j0 += 4) {
-    float4 gv[4];
-    uint32_t m1w[4], oldw[4], bases[4];
-    bool act[4];
+  for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
+    float4 gv[kBatch];
+    uint32_t m1w[kBatch], oldw[kBatch], bases[kBatch];
+    bool act[kBatch];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       bases[u] = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
       act[u] = bases[u] < n;
       if (act[u]) {
@@ -562,7 +563,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       if (!act[u]) continue;
       const uint32_t e0 = bases[u] + 4 * lane;
       const uint32_t widx = (bases[u] >> 5) + (lane >> 3);

@@ -168,12 +168,13 @@ class SparseConv2d(_MaskedLayer):
     super(SparseConv2d, self).__init__()
     k = int(kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size)
     s = int(strides[0] if isinstance(strides, (tuple, list)) else strides)
-    if padding not in ('SAME', 'VALID'):
-      raise ValueError('padding must be SAME or VALID')
+    if padding not in ('SAME', 'VALID', 'FIXED'):
+      raise ValueError('padding must be SAME, VALID or FIXED')
     self.ksize, self.stride = k, s
-    # conv2d_fixed_padding (resnet_model.py:234-303): explicit (k-1)//2 pad then VALID for
-    # stride>1; SAME for stride 1 -- both are a symmetric pad of (k-1)//2 for odd k.
-    self.pad = (k - 1) // 2 if padding == 'SAME' else 0
+    # 'FIXED' = conv2d_fixed_padding (resnet_model.py:234-303): explicit (k-1)//2 pad, then VALID.
+    # 'SAME'  = TensorFlow SAME: out = ceil(in/s), pad_before = pad_total // 2 (asymmetric for
+    #           stride 2 on even inputs -- what cifar_resnet/resnet_model.py:158-181 uses).
+    self.padding = padding
     self._setup(name or 'Conv', (k, k, int(in_channels), int(units)), device, registry,
                 kernel_initializer)
     self.patch_mode = (int(in_channels) % 8 != 0) and k > 1
@@ -191,12 +192,29 @@ class SparseConv2d(_MaskedLayer):
     else:
       super(SparseConv2d, self).pack()
 
+  @property
+  def pad(self):
+    """pad_before when it does not depend on the input size (FIXED / VALID / stride-1 SAME)."""
+    return 0 if self.padding == 'VALID' else (self.ksize - 1) // 2
+
+  def out_size(self, size):
+    """(output extent, pad_before) along one spatial dimension."""
+    k, s = self.ksize, self.stride
+    if self.padding == 'SAME':
+      out = (size + s - 1) // s
+      return out, max((out - 1) * s + k - size, 0) // 2
+    if self.padding == 'FIXED':
+      return (size + 2 * ((k - 1) // 2) - k) // s + 1, (k - 1) // 2
+    return (size - k) // s + 1, 0
+
   def _desc(self, n, h, w):
     d = _cabi.ConvDesc()
     d.batch, d.in_h, d.in_w, d.cin = n, h, w, self._cin
-    d.out_h = (h + 2 * self.pad - self.ksize) // self.stride + 1
-    d.out_w = (w + 2 * self.pad - self.ksize) // self.stride + 1
-    d.cout, d.ksize, d.stride, d.pad = self._cout, self.ksize, self.stride, self.pad
+    d.out_h, pad_h = self.out_size(h)
+    d.out_w, pad_w = self.out_size(w)
+    if pad_h != pad_w:
+      raise ValueError('unequal vertical/horizontal padding is not supported (%d vs %d)' % (pad_h, pad_w))
+    d.cout, d.ksize, d.stride, d.pad = self._cout, self.ksize, self.stride, pad_h
     d.x_pitch = 0
     return d
 
@@ -362,7 +380,7 @@ def sparse_conv2d(x, units, kernel_size, activation=None, use_bias=False, kernel
     elif sparsity_technique == 'baseline':
       k = kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size
       s = strides[0] if isinstance(strides, (tuple, list)) else strides
-      layer = nn.Conv2d(x.shape[1], units, k, stride=s, padding=(k - 1) // 2 if padding == 'SAME' else 0,
+      layer = nn.Conv2d(x.shape[1], units, k, stride=s, padding=(k - 1) // 2 if padding != 'VALID' else 0,
                         bias=use_bias, device=x.device, dtype=x.dtype)
     else:
       raise ValueError('Unsupported sparsity technique {}'.format(sparsity_technique))

@@ -35,7 +35,7 @@ class _Bottleneck(nn.Module):
 
   def __init__(self, cin, filters, strides, use_projection, name, device, registry):
     super(_Bottleneck, self).__init__()
-    mk = lambda ci, co, k, s, n: SparseConv2d(ci, co, k, strides=s, name='resnet_model/' + n,
+    mk = lambda ci, co, k, s, n: SparseConv2d(ci, co, k, strides=s, padding='FIXED', name='resnet_model/' + n,
                                               device=device, registry=registry)
     self.proj = None
     if use_projection:
@@ -64,7 +64,7 @@ class ResNet50(nn.Module):
     super(ResNet50, self).__init__()
     self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
     reg = self.registry
-    self.initial_conv = SparseConv2d(3, 64, 7, strides=2, name='resnet_model/initial_conv',
+    self.initial_conv = SparseConv2d(3, 64, 7, strides=2, padding='FIXED', name='resnet_model/initial_conv',
                                      device=device, registry=reg)
     self.initial_bn = _BNReLU(64, device=device)
     blocks = []
@@ -88,6 +88,94 @@ class ResNet50(nn.Module):
       x = blk(x)
     x = x.mean(dim=(2, 3))
     return self.final_dense(x)
+
+
+class WideResNet(nn.Module):
+  """Pre-activation WideResNet-(6n+4)-k, cifar_resnet/resnet_model.py:70-235 (BASELINE C5:
+  depth 22, width 2).  `conv_1` (3x3x3x16) is a plain dense conv unless prune_first_layer
+  (resnet_train_eval.py:96); residual 3x3 convs use TF 'SAME', the 1x1 skip convs 'VALID'
+  with the block stride; dropout 0.3 between the two convs of a block."""
+
+  def __init__(self, depth=22, width=2, num_classes=10, droprate=0.3, device='cuda', registry=None):
+    super(WideResNet, self).__init__()
+    if (depth - 4) % 6 != 0:
+      raise ValueError('Depth of ResNet specified not sufficient.')
+    self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
+    reg, n_blocks = self.registry, (depth - 4) // 6
+    self.conv_1 = nn.Conv2d(3, 16, 3, padding=1, bias=False, device=device, dtype=torch.bfloat16)
+    self.droprate = droprate
+    blocks, cin = [], 16
+    for name, size, subsample in (('conv_2', 16 * width, False), ('conv_3', 32 * width, True),
+                                  ('conv_4', 64 * width, True)):
+      for n in range(n_blocks):
+        stride = 2 if (subsample and n == 0) else 1
+        blk = nn.Module()
+        blk.bn_a = _BNReLU(cin, device=device)
+        blk.skip = None
+        if cin != size:
+          blk.skip = SparseConv2d(cin, size, 1, strides=stride, padding='VALID',
+                                  name='resnet_model/skip_%s' % name, device=device, registry=reg)
+        blk.conv_a = SparseConv2d(cin, size, 3, strides=stride, padding='SAME',
+                                  name='resnet_model/%s_%d_1' % (name, n), device=device, registry=reg)
+        blk.bn_b = _BNReLU(size, device=device)
+        blk.conv_b = SparseConv2d(size, size, 3, strides=1, padding='SAME',
+                                  name='resnet_model/%s_%d_2' % (name, n), device=device, registry=reg)
+        blocks.append(blk)
+        cin = size
+    self.blocks = nn.ModuleList(blocks)
+    self.final_bn = _BNReLU(cin, device=device)
+    self.logits = SparseLinear(cin, num_classes, name='resnet_model/logits', device=device, registry=reg,
+                               out_dtype=torch.float32)
+
+  def forward(self, x):
+    net = self.conv_1(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    for blk in self.blocks:
+      skip = net
+      net = blk.bn_a(net)
+      if blk.skip is not None:
+        skip = blk.skip(net)
+      net = blk.conv_a(net)
+      net = F.dropout(blk.bn_b(net), self.droprate, self.training)
+      net = blk.conv_b(net) + skip
+    net = self.final_bn(net)
+    return self.logits(net.mean(dim=(2, 3)))
+
+
+class MobileNetV1(nn.Module):
+  """MobileNet-v1 as the reference sparsifies it (mobilenetv1_model.py:156-342, BASELINE C4):
+  only the 13 pointwise 1x1 convs and `final_dense` are masked; `initial_conv` and the
+  depthwise 3x3 convs are dense (stock grouped convs)."""
+
+  CFG = ((64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1), (512, 1), (512, 1), (512, 1),
+         (512, 1), (1024, 2), (1024, 1))
+
+  def __init__(self, num_classes=1000, device='cuda', registry=None):
+    super(MobileNetV1, self).__init__()
+    self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
+    reg = self.registry
+    self.initial_conv = nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False, device=device, dtype=torch.bfloat16)
+    self.initial_bn = _BNReLU(32, device=device)
+    blocks, cin = [], 32
+    for i, (filters, stride) in enumerate(self.CFG):
+      blk = nn.Module()
+      blk.depthwise = nn.Conv2d(cin, cin, 3, stride=stride, padding=1, groups=cin, bias=False, device=device,
+                                dtype=torch.bfloat16)
+      blk.bn_dw = _BNReLU(cin, device=device)
+      blk.pointwise = SparseConv2d(cin, filters, 1, strides=1, padding='FIXED',
+                                   name='resnet_model/contraction_1x1_%d' % i, device=device, registry=reg)
+      blk.bn_pw = _BNReLU(filters, device=device)
+      blocks.append(blk)
+      cin = filters
+    self.blocks = nn.ModuleList(blocks)
+    self.final_dense = SparseLinear(cin, num_classes, name='resnet_model/final_dense', device=device,
+                                    registry=reg, out_dtype=torch.float32)
+
+  def forward(self, x):
+    x = self.initial_bn(self.initial_conv(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)))
+    for blk in self.blocks:
+      x = blk.bn_dw(blk.depthwise(x))
+      x = blk.bn_pw(blk.pointwise(x))
+    return self.final_dense(x.mean(dim=(2, 3)))
 
 
 class MnistFC(nn.Module):

@@ -51,16 +51,23 @@ CONV_CASES = [
     (4, 28, 28, 128, 128, 3, 2, 0.82),
     (16, 7, 7, 256, 256, 3, 1, 0.95),
     (32, 7, 7, 512, 128, 1, 1, 0.7),
+    # TensorFlow 'SAME' incl. the asymmetric stride-2 case (WRN, cifar_resnet/resnet_model.py:158-181)
+    (4, 32, 32, 16, 32, 3, 2, 0.8, 'SAME'),
+    (2, 16, 16, 64, 128, 3, 2, 0.9, 'SAME'),
+    (2, 15, 15, 32, 64, 3, 2, 0.5, 'SAME'),
+    (2, 16, 16, 32, 64, 1, 2, 0.2, 'VALID'),
+    (2, 9, 9, 16, 16, 3, 1, 0.3, 'VALID'),
 ]
 
 
 def _conv_case(case, force_simt):
-  n, h, w, cin, cout, k, stride, sparsity = case
-  rng = np.random.RandomState(hash(case) % (2 ** 31))
+  n, h, w, cin, cout, k, stride, sparsity = case[:8]
+  padding = case[8] if len(case) > 8 else 'FIXED'
+  rng = np.random.RandomState(abs(hash(case[:8])) % (2 ** 31))
   pruning.reset_default_registry()
   _cabi.lib().rigl_set_force_simt(1 if force_simt else 0)
   try:
-    layer = SparseConv2d(cin, cout, k, strides=stride, name='t', device=DEV)
+    layer = SparseConv2d(cin, cout, k, strides=stride, padding=padding, name='t', device=DEV)
     w_np = _bf16(rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).float().numpy()
     m_np = orc.get_mask_random_numpy((k, k, cin, cout), sparsity, rng).astype(np.float32)
     with torch.no_grad():
@@ -71,15 +78,17 @@ def _conv_case(case, force_simt):
         .contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y = layer(x)
     wm = (w_np * m_np).astype(np.float64)
-    pad = (k - 1) // 2
-    y_want = orc.conv2d_nhwc_fwd(x_np.astype(np.float64), wm, stride, pad)
+    (ho, pad), (wo, _) = layer.out_size(h), layer.out_size(w)
+    if padding == 'SAME':
+      assert (ho, pad) == orc.tf_same_padding(h, k, stride)[:2]
+    y_want = orc.conv2d_nhwc_general(x_np.astype(np.float64), wm, stride, pad, (ho, wo))
     assert tuple(y.shape) == (n, cout, y_want.shape[1], y_want.shape[2])
     _check_bf16(y.permute(0, 2, 3, 1), y_want, 'fprop %s' % (case,))
     dy_np = _bf16(rng.standard_normal(y_want.shape)).float().numpy()
     dy = torch.from_numpy(dy_np).permute(0, 3, 1, 2).to(DEV).to(torch.bfloat16) \
         .contiguous(memory_format=torch.channels_last)
     y.backward(dy)
-    dx_want, dw_want = orc.conv2d_nhwc_bwd(x_np.astype(np.float64), wm, dy_np.astype(np.float64), stride, pad)
+    dx_want, dw_want = orc.conv2d_nhwc_general_bwd(x_np.astype(np.float64), wm, dy_np.astype(np.float64), stride, pad)
     _check_bf16(x.grad.permute(0, 2, 3, 1), dx_want, 'dgrad %s' % (case,))
     # dense wgrad: every position, including masked-out ones (RigL grow scores)
     _check_f32(layer.masked_weights.dense_grad.view(k, k, cin, cout), dw_want, 'wgrad %s' % (case,))

@@ -93,3 +93,43 @@ def test_mnist_fc_trains():
     last = float(h.step(x, y))
   assert last < 0.7 * first
   assert [m.count_ones() for m in model.registry.get_masks()] == [23520, 5700, 1000]
+
+
+def test_wrn22_2_layer_table_and_step(golden):
+  """BASELINE C5 workload: names/shapes/ERK-0.95 counts equal the reference-generated fixture."""
+  torch.manual_seed(4)
+  model = workloads.WideResNet(depth=22, width=2, device=DEV)
+  case = [c for c in golden['cases'] if c['tag'] == 'wrn22_2_erk95'][0]
+  got = sorted((m.name, list(m.shape)) for m in model.registry.get_masks())
+  want = sorted((n + '/mask:0', sh) for n, sh in case['layers'])
+  assert got == want
+  sp = workloads.init_masks(model, 'erdos_renyi_kernel', 0.95, seed=4)
+  for m in model.registry.get_masks():
+    assert float(sp[m.name]).hex() == case['sparsities_hex'][m.name] and m.count_ones() == case['nnz'][m.name]
+  h = workloads.TrainHarness(model, lr=0.1, weight_decay=5e-4, label_smoothing=0.0, frequency=100, end_step=75000)
+  x = torch.randn(32, 3, 32, 32, device=DEV)
+  y = torch.randint(0, 10, (32,), device=DEV)
+  losses = [float(h.step(x, y).detach()) for _ in range(6)]
+  assert all(np.isfinite(losses)) and h.global_step.value == 5        # step 0 was the mask update
+  assert [m.count_ones() for m in model.registry.get_masks()] == \
+      [case['nnz'][m.name] for m in model.registry.get_masks()]
+
+
+def test_mobilenet_v1_masked_pointwise_step(golden):
+  """BASELINE C4 workload: 13 pointwise convs + classifier masked at 0.9 (overall ~0.89)."""
+  torch.manual_seed(5)
+  model = workloads.MobileNetV1(device=DEV)
+  case = [c for c in golden['cases'] if c['tag'] == 'mobilenetv1_uniform90'][0]
+  assert [(m.name, list(m.shape)) for m in model.registry.get_masks()] == \
+      [(n + '/mask:0', sh) for n, sh in case['layers']]
+  workloads.init_masks(model, 'random', 0.9, seed=5)
+  assert [m.count_ones() for m in model.registry.get_masks()] == [case['nnz'][m.name] for m in model.registry.get_masks()]
+  h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
+  x = torch.randn(8, 3, 64, 64, device=DEV)
+  y = torch.randint(0, 1000, (8,), device=DEV)
+  incs = []
+  for _ in range(4):
+    before = h.global_step.value
+    assert np.isfinite(float(h.step(x, y).detach()))
+    incs.append(h.global_step.value - before)
+  assert incs == [0, 1, 1, 0]

@@ -81,7 +81,7 @@ def main():
     torch.manual_seed(hash(case) % 100000)
     pruning.reset_default_registry()
     try:
-      layer = SparseConv2d(cin, cout, k, strides=stride, name='t', device=DEV)
+      layer = SparseConv2d(cin, cout, k, strides=stride, padding='FIXED', name='t', device=DEV)
       layer.mask.assign((torch.rand(k, k, cin, cout, device=DEV) >= sparsity).float())
       x = torch.randn(n, cin, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
       ho = (h + 2 * layer.pad - k) // stride + 1
