@@ -250,27 +250,36 @@ def run_ours(args):
     dist.destroy_process_group()
 
 
-def _use_all_host_threads():
-  """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
-  n = os.cpu_count() or 1
-  try:
-    n = len(os.sched_getaffinity(0))
-  except AttributeError:
-    pass
-  torch.set_num_threads(max(1, n))
+def _cpu_port_timing(batch, steps, warmup):
+  """Times the CPU port in a FRESH interpreter whose OpenMP environment is not the one
+  torchrun exports (OMP_NUM_THREADS=1): torch then sizes its intra-op pool to the host's
+  cores.  Returns {'sec_per_step', 'mask_update_sec', 'threads'}."""
+  env = dict(os.environ)
+  for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OMP_PROC_BIND', 'OMP_PLACES', 'GOMP_CPU_AFFINITY',
+            'KMP_AFFINITY', 'CUDA_VISIBLE_DEVICES'):
+    env.pop(k, None)
+  env['CUDA_VISIBLE_DEVICES'] = ''
+  code = ('import json,sys,torch; sys.path.insert(0, %r); '
+          'from oracle import cpu_train_step as c; '
+          's, net, dense = c.time_train_steps(%d, %d, warmup=%d); '
+          'mu = c.time_mask_update(net, dense); '
+          'print("CPUPORT " + json.dumps({"sec_per_step": s, "mask_update_sec": mu, '
+          '"threads": torch.get_num_threads()}))' % (ROOT, batch, steps, warmup))
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=1500)
+  for line in out.stdout.splitlines():
+    if line.startswith('CPUPORT '):
+      return json.loads(line[len('CPUPORT '):])
+  raise RuntimeError('CPU port failed: ' + out.stderr[-2000:])
 
 
 def cpu_baseline_leg(sample_batch=16, steps=1):
   """Times the CPU port of the reference path on the host cores (bounded sample)."""
-  from oracle import cpu_train_step as cpu
-  _use_all_host_threads()
-  threads = torch.get_num_threads()
-  sec, net, dense = cpu.time_train_steps(sample_batch, steps, warmup=1)
-  mu = cpu.time_mask_update(net, dense)
-  return {'value': sample_batch / sec, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
+  t = _cpu_port_timing(sample_batch, steps, 1)
+  return {'value': sample_batch / t['sec_per_step'], 'unit': 'images/sec', 'cores': t['threads'], 'kind': 'port',
           'sample': 'ResNet-50 80%% ERK fp32 train step (fwd + dense&masked bwd + momentum), batch %d, '
                     '%d timed step(s) after 1 warm-up, torch-CPU port of the TF1 graph' % (sample_batch, steps),
-          'mask_update_ms': mu * 1e3,
+          'mask_update_ms': t['mask_update_sec'] * 1e3,
           'mask_update_sample': 'one drop/grow update of all 54 layers (numpy stable argsort x2 per layer)'}
 
 
@@ -280,15 +289,12 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  from oracle import cpu_train_step as cpu
-  _use_all_host_threads()
-  threads = torch.get_num_threads()
   batch = args.cpu_batch
   steps = max(1, min(args.steps, 3))
   warm = max(1, min(args.warmup, 1))
   t0 = time.perf_counter()
-  sec, net, dense = cpu.time_train_steps(batch, steps, warmup=warm)
-  mu = cpu.time_mask_update(net, dense)
+  t = _cpu_port_timing(batch, steps, warm)
+  sec, mu, threads = t['sec_per_step'], t['mask_update_sec'], t['threads']
   value = batch / sec
   print(json.dumps({
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/sec',
