@@ -613,7 +613,9 @@ static size_t wgrad_ws_elems(const ConvGeom& g, int* splits_out, int* bps_out, i
   return (size_t)splits * g.taps() * g.cin * g.cout;
 }
 
-static int wgrad_bn_tile(const ConvGeom& g) { return g.cout >= 128 ? 128 : 64; }
+// Wider N tiles halve the L2->smem bytes per FLOP (the wgrad main loop is L2-bandwidth bound:
+// K blocks are only 64 pixels deep).
+static int wgrad_bn_tile(const ConvGeom& g) { return g.cout >= 256 ? 256 : (g.cout >= 128 ? 128 : 64); }
 
 size_t tc_workspace_bytes(const ConvGeom& g) {
   if (!tc_supported(g, 2)) return 0;
@@ -834,7 +836,9 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
   CUtensorMap dymap;
   rc = make_act_map(&dymap, dy, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, box);
   if (rc != RIGL_OK) return rc;
-  rc = (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s) : launch_wgrad<64, 8>(xmaps, dymap, p, s);
+  rc = (bn_tile == 256)   ? launch_wgrad<256, 4>(xmaps, dymap, p, s)
+       : (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s)
+                          : launch_wgrad<64, 8>(xmaps, dymap, p, s);
   if (rc != RIGL_OK) return rc;
   if (!direct) {
     const long long threads = (n_w + 3) / 4;
