@@ -174,6 +174,24 @@ RIGL_API int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, con
  * runs as a masked dense layer over [pixels, k*k*cin] with the SAME HWIO weights and mask. */
 RIGL_API int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* out, int64_t out_pitch,
                               void* stream);
+/* Small-Cin convs (cin <= 8, ksize <= 8: the 7x7x3 stem, resnet_model.py:620-633) WITHOUT a
+ * patch matrix: the input is copied once into a zero-bordered 8-channel buffer `xp`
+ * (rigl_smallc_padded_bytes); window tensor maps with a W stride of `stride` pixels then feed
+ * the same tcgen05 kernels with ksize "taps" of K = 64 = 8 pixels x 8 channels.  `packed` here
+ * is the stem-specific operand written by rigl_smallc_pack_weights from the SAME HWIO weights
+ * and mask.  dw is the dense HWIO gradient as in rigl_conv2d_wgrad_dense. */
+RIGL_API int rigl_smallc_supported(const rigl_conv_desc* d);
+RIGL_API size_t rigl_smallc_padded_bytes(const rigl_conv_desc* d);
+RIGL_API size_t rigl_smallc_packed_bytes(const rigl_conv_desc* d);
+RIGL_API size_t rigl_smallc_workspace_bytes(const rigl_conv_desc* d);
+RIGL_API int rigl_smallc_pad_input(const rigl_conv_desc* d, const void* x, void* xp, void* stream);
+RIGL_API int rigl_smallc_pack_weights(const rigl_conv_desc* d, const float* w_hwio,
+                                      const uint32_t* mask_bits, void* packed, void* stream);
+RIGL_API int rigl_smallc_fprop(const rigl_conv_desc* d, const void* xp, const void* packed, void* y,
+                               void* stream);
+RIGL_API int rigl_smallc_wgrad(const rigl_conv_desc* d, const void* xp, const void* dy, float* dw,
+                               float beta, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------
  * Fused batch-norm (+ReLU, +residual) over NHWC bf16 activations viewed as [rows, channels]
  * Replaces batch_norm_relu (rigl/imagenet_resnet/resnet_model.py:41-80) and the

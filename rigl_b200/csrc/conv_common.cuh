@@ -61,4 +61,15 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
 int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, void* ws,
              size_t ws_bytes, cudaStream_t s);
 
+// small-Cin (stem) path (igemm_tc.cu)
+bool smallc_supported(const ConvGeom& g);
+size_t smallc_padded_bytes(const ConvGeom& g);
+size_t smallc_packed_bytes(const ConvGeom& g);
+size_t smallc_wgrad_ws_bytes(const ConvGeom& g);
+int smallc_pad_input(const ConvGeom& g, const void* x, void* xp, cudaStream_t s);
+int smallc_pack(const ConvGeom& g, const float* w, const uint32_t* bits, void* packed, cudaStream_t s);
+int smallc_fprop(const ConvGeom& g, const void* xp, const void* packed, void* y, cudaStream_t s);
+int smallc_wgrad(const ConvGeom& g, const void* xp, const void* dy, float* dw, float beta, void* ws,
+                 size_t ws_bytes, cudaStream_t s);
+
 }  // namespace rigl

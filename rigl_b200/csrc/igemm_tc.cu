@@ -84,7 +84,12 @@ __device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_
 // ----------------------------------------------------------------------------
 // fprop / dgrad kernel: D[128 pixels, BN] += A[128, 64] * B[BN, 64]^T per (tap, k block)
 // ----------------------------------------------------------------------------
-template <int BN, int STAGES>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs work on the two M tiles of a tile
+// PAIR that share the weight tile: each loads HALF of B and multicasts it into both CTAs'
+// shared memory, which cuts the L2->smem bytes per FLOP by a third (these kernels are bound
+// by that traffic, not by the tensor pipe).  A stage is recycled only when BOTH consumers
+// have released it (empty barriers count CL arrivals; tcgen05.commit multicasts them).
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUtensorMap bmap,
                const __grid_constant__ CUtensorMap omap, const IgemmParams p) {
@@ -112,27 +117,33 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
     prefetch_tmap(&bmap);
     if (p.tma_store) prefetch_tmap(&omap);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();       // peers' barriers are live before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Tile schedule: a "pair" = CL consecutive M tiles x one N tile; pairs are dealt round-robin to
+  // clusters, N fastest (neighbouring clusters reuse the same activation tiles in L2).
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int m_pairs = (m_tiles + CL - 1) / CL;
+  const int total_pairs = m_pairs * p.n_tiles;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   constexpr int kBN64 = (BN + 63) / 64;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+      for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+        const int n_tile = pair % p.n_tiles;
+        const int m_tile = (pair / p.n_tiles) * CL + (int)cta_rank;   // may exceed m_tiles: loads zero-fill, stores clip
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
@@ -148,7 +159,12 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
             mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
             tma_load_4d(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
                         th * p.bh + tap.dh, tn * p.bn);
-            tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN, tap.b_tap);
+            if (CL > 1) {     // my half of the weight tile, multicast to every CTA of the cluster
+              tma_load_3d_mc(b_dst + cta_rank * (uint32_t)(BN / CL) * 128u, &bmap, full_bar(stage), kb * kBK,
+                             n_tile * BN + (int)cta_rank * (BN / CL), tap.b_tap, kMcMask);
+            } else {
+              tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN, tap.b_tap);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -159,8 +175,8 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
+      for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+        const int n_tile = pair % p.n_tiles;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -179,7 +195,8 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
               umma_bf16(d_tmem, da, db, kIdesc, (first && k == 0) ? 0u : 1u);
             }
             first = false;
-            umma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
+            if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);   // release the slot in BOTH CTAs
+            else umma_commit(empty_bar(stage));            // frees the smem slot when the MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -193,9 +210,9 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     const int row = quad * 32 + lane;                     // pixel index inside the box
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t slab_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+      const int n_tile = pair % p.n_tiles;
+      const int m_tile = (pair / p.n_tiles) * CL + (int)cta_rank;
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int tn = m_tile / (p.tiles_w * p.tiles_h);
@@ -308,7 +325,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();    // no CTA exits while a peer may still signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -331,7 +348,10 @@ struct WgradParams {
   long long split_stride;           // elements between split slices
 };
 
-template <int BN, int STAGES>
+// CL = CTAs per cluster (1 or 2).  The dY tile depends only on (pixel block, N tile), so with
+// CL == 2 two work units that differ in (tap, M tile) share it: each CTA fetches half of the dY
+// boxes and multicasts them to both (same protocol as k_igemm_kmajor).
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUtensorMap dymap,
               const WgradParams p) {
@@ -342,6 +362,9 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
   constexpr uint32_t kBox = 64 * 64 * 2;             // 8 KB: 64 pixels x 64 channels
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 1, 1);
+  constexpr int kBBoxes = BN / 64;
+  static_assert(CL == 1 || kBBoxes % CL == 0, "multicast splits the dY boxes between the CTAs");
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * kStageBytes;
@@ -357,28 +380,37 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&xmaps.a[i]);
     prefetch_tmap(&dymap);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int out_tiles = p.ntaps * p.m_tiles * p.n_tiles;
-  const int total_units = out_tiles * p.splits;
+  // Work units: (split, N tile, M index) with M index = tap * m_tiles + m_tile; a cluster takes
+  // CL consecutive M indices of one (split, N tile).  Indices past the end are idle partners:
+  // their x boxes are requested out of bounds (zero fill) and nothing is stored.
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int mcount = p.ntaps * p.m_tiles;
+  const int m_groups = (mcount + CL - 1) / CL;
+  const int groups_per_split = m_groups * p.n_tiles;
+  const int total_groups = groups_per_split * p.splits;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int split = u / out_tiles;
-        const int ot = u % out_tiles;
-        const int n_tile = ot % p.n_tiles;
-        const int m_tile = (ot / p.n_tiles) % p.m_tiles;
-        const TapInfo tap = p.taps[ot / (p.n_tiles * p.m_tiles)];
+      for (int q = cluster_id; q < total_groups; q += n_clusters) {
+        const int split = q / groups_per_split;
+        const int r = q % groups_per_split;
+        const int n_tile = r % p.n_tiles;
+        const int mi = (r / p.n_tiles) * CL + (int)cta_rank;
+        const bool live = mi < mcount;
+        const TapInfo tap = p.taps[live ? mi / p.m_tiles : 0];
+        const int c_base = live ? (mi % p.m_tiles) * kBM : (1 << 28);     // idle partner: out of bounds
         const int pb0 = split * p.pblocks_per_split;
         const int pb1 = min(pb0 + p.pblocks_per_split, p.pblocks);
         for (int pb = pb0; pb < pb1; ++pb) {
@@ -391,12 +423,21 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
 #pragma unroll
           for (int h = 0; h < kBM / 64; ++h)
-            tma_load_4d(a_dst + h * kBox, &xmaps.a[tap.map_id], full_bar(stage), m_tile * kBM + h * 64,
+            tma_load_4d(a_dst + h * kBox, &xmaps.a[tap.map_id], full_bar(stage), c_base + h * 64,
                         tw * p.bw + tap.dw, th * p.bh + tap.dh, tn * p.bn);
+          if (CL > 1) {
 #pragma unroll
-          for (int h = 0; h < BN / 64; ++h)
-            tma_load_4d(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
-                        th * p.bh, tn * p.bn);
+            for (int hh = 0; hh < kBBoxes / CL; ++hh) {
+              const int h = (int)cta_rank * (kBBoxes / CL) + hh;
+              tma_load_4d_mc(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
+                             th * p.bh, tn * p.bn, kMcMask);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < kBBoxes; ++h)
+              tma_load_4d(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
+                          th * p.bh, tn * p.bn);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -405,8 +446,8 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int split = u / out_tiles;
+      for (int q = cluster_id; q < total_groups; q += n_clusters) {
+        const int split = q / groups_per_split;
         const int pb0 = split * p.pblocks_per_split;
         const int pb1 = min(pb0 + p.pblocks_per_split, p.pblocks);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -424,7 +465,8 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
             const uint64_t db = make_smem_desc(b_src + k * 16 * 128, kBox, 1024);
             umma_bf16(d_tmem, da, db, kIdesc, (pb == pb0 && k == 0) ? 0u : 1u);
           }
-          umma_commit(empty_bar(stage));
+          if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
@@ -435,21 +477,22 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int split = u / out_tiles;
-      const int ot = u % out_tiles;
-      const int n_tile = ot % p.n_tiles;
-      const int m_tile = (ot / p.n_tiles) % p.m_tiles;
-      const int tap_idx = ot / (p.n_tiles * p.m_tiles);
-      const int ci = m_tile * kBM + row;
+    for (int q = cluster_id; q < total_groups; q += n_clusters) {
+      const int split = q / groups_per_split;
+      const int r = q % groups_per_split;
+      const int n_tile = r % p.n_tiles;
+      const int mi = (r / p.n_tiles) * CL + (int)cta_rank;
+      const bool live = mi < mcount;
+      const int tap_idx = live ? mi / p.m_tiles : 0;
+      const int ci = live ? (mi % p.m_tiles) * kBM + row : p.ci;          // idle partner stores nothing
       float* dst_row = p.out + (long long)split * p.split_stride +
                        ((long long)p.taps[tap_idx].b_tap * p.ci + ci) * p.co;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        uint32_t r32[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r32);
         tmem_ld_wait();
         const int co0 = n_tile * BN + c0;
         if (ci < p.ci && co0 < p.co) {
@@ -457,10 +500,10 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
           for (int j = 0; j < 32; j += 4) {
             if (co0 + j + 4 <= p.co) {
               *reinterpret_cast<float4*>(dst_row + co0 + j) =
-                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                              __uint_as_float(r[j + 3]));
+                  make_float4(__uint_as_float(r32[j]), __uint_as_float(r32[j + 1]), __uint_as_float(r32[j + 2]),
+                              __uint_as_float(r32[j + 3]));
             } else {
-              for (int q = 0; q < 4 && co0 + j + q < p.co; ++q) dst_row[co0 + j + q] = __uint_as_float(r[j + q]);
+              for (int t = 0; t < 4 && co0 + j + t < p.co; ++t) dst_row[co0 + j + t] = __uint_as_float(r32[j + t]);
             }
           }
         }
@@ -472,7 +515,7 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -509,6 +552,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
+static bool g_cluster_mc = true;    // RIGL_CLUSTER_MC=0 disables the 2-CTA weight-tile multicast
 static int g_num_sms = 0;
 static std::once_flag g_once;
 static int g_init_status = RIGL_OK;
@@ -524,6 +568,7 @@ static void init_driver() {
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* e = getenv("RIGL_TMA_STORE")) g_tma_store = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = !(e[0] == '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -624,18 +669,36 @@ size_t tc_workspace_bytes(const ConvGeom& g) {
   return wgrad_ws_elems(g, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g)) * sizeof(float) + 256;
 }
 
-template <int BN, int STAGES>
+// With the 2-CTA multicast each CTA fetches half of the weight tile (B box = bn_tile/2 rows).
+static bool kmajor_use_mc(const IgemmParams& p) {
+  return g_cluster_mc && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
+}
+static int kmajor_b_rows(const IgemmParams& p, int bn_tile) { return kmajor_use_mc(p) ? bn_tile / 2 : bn_tile; }
+
+template <int BN, int STAGES, int CL>
 static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap, const IgemmParams& p,
                          cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 2 * (kBM * 64 * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  k_igemm_kmajor<BN, STAGES><<<grid, kThreads, smem, s>>>(amaps, bmap, omap, p);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pairs = ((m_tiles + CL - 1) / CL) * p.n_tiles;
+  int clusters = g_num_sms / CL;
+  if (pairs < clusters) clusters = pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_kmajor<BN, STAGES, CL>, amaps, bmap, omap, p));
   RIGL_LAUNCH_CHECK("k_igemm_kmajor");
   return RIGL_OK;
 }
@@ -643,9 +706,10 @@ static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUt
 static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap,
                            IgemmParams& p, int bn_tile, cudaStream_t s) {
   p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
-  if (bn_tile == 64) return launch_kmajor<64, 8>(amaps, bmap, omap, p, s);
-  if (bn_tile == 128) return launch_kmajor<128, 6>(amaps, bmap, omap, p, s);
-  return launch_kmajor<256, 4>(amaps, bmap, omap, p, s);
+  const bool mc = kmajor_use_mc(p);                        // multicast needs a partner M tile
+  if (bn_tile == 64) return mc ? launch_kmajor<64, 8, 2>(amaps, bmap, omap, p, s) : launch_kmajor<64, 8, 1>(amaps, bmap, omap, p, s);
+  if (bn_tile == 128) return mc ? launch_kmajor<128, 6, 2>(amaps, bmap, omap, p, s) : launch_kmajor<128, 6, 1>(amaps, bmap, omap, p, s);
+  return mc ? launch_kmajor<256, 4, 2>(amaps, bmap, omap, p, s) : launch_kmajor<256, 4, 1>(amaps, bmap, omap, p, s);
 }
 
 static int pick_bn(int n_out, long long m_tiles) {
@@ -694,7 +758,7 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   CUtensorMap bmap;
   const uint64_t bdims[3] = {(uint64_t)L.cin_pad, (uint64_t)g.cout, (uint64_t)g.taps()};
   const uint64_t bstr[2] = {(uint64_t)L.cin_pad * 2, (uint64_t)g.cout * L.cin_pad * 2};
-  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
+  const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)kmajor_b_rows(p, bn_tile), 1};
   rc = make_tmap(&bmap, pk + L.off_fprop, 3, bdims, bstr, bbox);
   if (rc != RIGL_OK) return rc;
   CUtensorMap omap = bmap;
@@ -759,7 +823,7 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
       CUtensorMap bmap;
       const uint64_t bdims[3] = {(uint64_t)L.cout_pad, (uint64_t)g.cin, (uint64_t)g.taps()};
       const uint64_t bstr[2] = {(uint64_t)L.cout_pad * 2, (uint64_t)g.cin * L.cout_pad * 2};
-      const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)bn_tile, 1};
+      const uint32_t bbox[3] = {(uint32_t)kBK, (uint32_t)kmajor_b_rows(p, bn_tile), 1};
       rc = make_tmap(&bmap, pk + L.off_dgrad, 3, bdims, bstr, bbox);
       if (rc != RIGL_OK) return rc;
       CUtensorMap omap = bmap;
@@ -774,19 +838,39 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
   return RIGL_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_wgrad(const TMaps4& xmaps, const CUtensorMap& dymap, const WgradParams& p, cudaStream_t s) {
+template <int BN, int STAGES, int CL>
+static int launch_wgrad_cl(const TMaps4& xmaps, const CUtensorMap& dymap, const WgradParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_wgrad<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_wgrad<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int total = p.ntaps * p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  k_igemm_wgrad<BN, STAGES><<<grid, kThreads, smem, s>>>(xmaps, dymap, p);
+  const int mcount = p.ntaps * p.m_tiles;
+  const int groups = ((mcount + CL - 1) / CL) * p.n_tiles * p.splits;
+  int clusters = g_num_sms / CL;
+  if (groups < clusters) clusters = groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_wgrad<BN, STAGES, CL>, xmaps, dymap, p));
   RIGL_LAUNCH_CHECK("k_igemm_wgrad");
   return RIGL_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const TMaps4& xmaps, const CUtensorMap& dymap, const WgradParams& p, cudaStream_t s) {
+  if constexpr (BN >= 128) {
+    if (g_cluster_mc && p.ntaps * p.m_tiles >= 2) return launch_wgrad_cl<BN, STAGES, 2>(xmaps, dymap, p, s);
+  }
+  return launch_wgrad_cl<BN, STAGES, 1>(xmaps, dymap, p, s);
 }
 
 int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, void* ws, size_t ws_bytes,
@@ -845,6 +929,215 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
     k_splitk_reduce<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p.out, p.split_stride, p.splits, dw, n_w, beta);
     RIGL_LAUNCH_CHECK("k_splitk_reduce");
   }
+  return RIGL_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Small-Cin convs (the 7x7x3 stem) without a patch matrix.
+// The input is copied once into a zero-bordered, 8-channel-padded buffer xp[N,Hp,Wp,8]; for
+// filter row kh the K slice (kw, c) of an output pixel is then 64 CONTIGUOUS bf16 (8 pixels x
+// 8 channels) starting at pixel (s*wo, s*ho + kh): a tensor map whose W dimension has a
+// stride of s pixels (32 bytes for s = 2: overlapping windows) presents exactly that to TMA,
+// so the conv runs on the same k_igemm_kmajor / k_igemm_wgrad kernels with k "taps" of K = 64
+// and weights packed as [kh][co][kw*8 + c].  No im2col buffer, 216 MB instead of 1 GB of traffic.
+// ----------------------------------------------------------------------------
+struct SmallCGeom {
+  int hp, wp;        // padded input extents
+};
+
+static SmallCGeom smallc_geom(const ConvGeom& g) {
+  SmallCGeom q;
+  q.hp = (g.out_h - 1) * g.stride + g.ksize;
+  q.wp = (g.out_w - 1) * g.stride + 8;
+  return q;
+}
+
+__global__ void k_smallc_pad(ConvGeom g, int hp, int wp, const __nv_bfloat16* __restrict__ x,
+                             __nv_bfloat16* __restrict__ xp) {
+  const long long total = (long long)g.batch * hp * wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % wp), h = (int)((i / wp) % hp), n = (int)(i / ((long long)wp * hp));
+    const int hi = h - g.pad, wi = w - g.pad;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __float2bfloat16(0.f);
+    if (hi >= 0 && hi < g.in_h && wi >= 0 && wi < g.in_w) {
+      const __nv_bfloat16* src = x + (((long long)n * g.in_h + hi) * g.in_w + wi) * g.x_pitch;
+      for (int c = 0; c < g.cin; ++c) v[c] = src[c];
+    }
+    reinterpret_cast<uint4*>(xp)[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// packed[kh][co][kw*8 + c] = mask ? w[kh,kw,c,co] : 0   (zero for c >= cin, kw >= k)
+__global__ void k_smallc_pack(ConvGeom g, const float* __restrict__ w, const uint32_t* __restrict__ bits,
+                              __nv_bfloat16* __restrict__ out) {
+  const int total = g.ksize * g.cout * 64;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kk = i % 64, co = (i / 64) % g.cout, kh = i / (64 * g.cout);
+  const int kw = kk >> 3, c = kk & 7;
+  float v = 0.f;
+  if (kw < g.ksize && c < g.cin) {
+    const long long e = (((long long)kh * g.ksize + kw) * g.cin + c) * g.cout + co;
+    if ((bits[e >> 5] >> (e & 31)) & 1u) v = w[e];
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+// dw_hwio[kh,kw,c,co] = beta*dw + sum_s part[s][kh][kw*8+c][co]
+__global__ void k_smallc_unpack(ConvGeom g, const float* __restrict__ part, long long split_stride, int splits,
+                                float* __restrict__ dw, float beta) {
+  const long long total = (long long)g.ksize * g.ksize * g.cin * g.cout;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int co = (int)(e % g.cout), c = (int)((e / g.cout) % g.cin);
+  const int kw = (int)((e / ((long long)g.cout * g.cin)) % g.ksize), kh = (int)(e / ((long long)g.cout * g.cin * g.ksize));
+  const long long src = ((long long)kh * 64 + kw * 8 + c) * g.cout + co;
+  float a = beta != 0.f ? dw[e] : 0.f;
+  for (int s = 0; s < splits; ++s) a += part[(long long)s * split_stride + src];
+  dw[e] = a;
+}
+
+bool smallc_supported(const ConvGeom& g) {
+  return g.cin <= 8 && g.ksize <= 8 && g.ksize >= 2 && g.cout % 8 == 0 && (g.stride == 1 || g.stride == 2);
+}
+
+size_t smallc_padded_bytes(const ConvGeom& g) {
+  const SmallCGeom q = smallc_geom(g);
+  return (size_t)g.batch * q.hp * q.wp * 16;
+}
+
+size_t smallc_packed_bytes(const ConvGeom& g) { return (size_t)g.ksize * g.cout * 64 * 2; }
+
+int smallc_pad_input(const ConvGeom& g, const void* x, void* xp, cudaStream_t s) {
+  const SmallCGeom q = smallc_geom(g);
+  k_smallc_pad<<<148 * 16, 256, 0, s>>>(g, q.hp, q.wp, (const __nv_bfloat16*)x, (__nv_bfloat16*)xp);
+  RIGL_LAUNCH_CHECK("k_smallc_pad");
+  return RIGL_OK;
+}
+
+int smallc_pack(const ConvGeom& g, const float* w, const uint32_t* bits, void* packed, cudaStream_t s) {
+  const int total = g.ksize * g.cout * 64;
+  k_smallc_pack<<<(total + 255) / 256, 256, 0, s>>>(g, w, bits, (__nv_bfloat16*)packed);
+  RIGL_LAUNCH_CHECK("k_smallc_pack");
+  return RIGL_OK;
+}
+
+// Window view of xp for filter rows kh == parity (mod stride): dims (64, out_w, rows, N).
+static int make_window_map(CUtensorMap* out, const void* xp, const ConvGeom& g, const SmallCGeom& q, int parity,
+                           const uint32_t box[4]) {
+  const uint64_t rows = (q.hp - parity + g.stride - 1) / g.stride;
+  const uint64_t dims[4] = {64, (uint64_t)g.out_w, rows, (uint64_t)g.batch};
+  const uint64_t strides[3] = {(uint64_t)g.stride * 16, (uint64_t)g.stride * q.wp * 16, (uint64_t)q.hp * q.wp * 16};
+  const uint8_t* base = static_cast<const uint8_t*>(xp) + (size_t)parity * q.wp * 16;
+  return make_tmap(out, base, 4, dims, strides, box);
+}
+
+int smallc_fprop(const ConvGeom& g, const void* xp, const void* packed, void* y, cudaStream_t s) {
+  int rc = ensure_driver();
+  if (rc != RIGL_OK) return rc;
+  const SmallCGeom q = smallc_geom(g);
+  IgemmParams p = {};
+  choose_box(g.out_w, g.out_h, g.batch, 128, &p.bw, &p.bh, &p.bn);
+  p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
+  p.tiles_w = (p.GW + p.bw - 1) / p.bw; p.tiles_h = (p.GH + p.bh - 1) / p.bh; p.tiles_n = (p.NB + p.bn - 1) / p.bn;
+  p.kblks = 1;
+  p.N = g.cout;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(y);
+  p.o_off = 0; p.o_sw = g.cout; p.o_sh = (long long)g.out_w * g.cout; p.o_sn = (long long)g.out_h * g.out_w * g.cout;
+  p.nnz = nullptr;
+  TMaps4 amaps;
+  const uint32_t abox[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  for (int par = 0; par < g.stride; ++par) {
+    rc = make_window_map(&amaps.a[par], xp, g, q, par, abox);
+    if (rc != RIGL_OK) return rc;
+  }
+  for (int i = g.stride; i < 4; ++i) amaps.a[i] = amaps.a[0];
+  p.ntaps = g.ksize;
+  for (int kh = 0; kh < g.ksize; ++kh) {
+    TapInfo& t = p.taps[kh];
+    t.map_id = (int8_t)(kh % g.stride); t.dh = (int8_t)(kh / g.stride); t.dw = 0; t.b_tap = kh;
+  }
+  const int bn_tile = pick_bn(g.cout, (long long)p.tiles_w * p.tiles_h * p.tiles_n);
+  CUtensorMap bmap;
+  const uint64_t bdims[3] = {64, (uint64_t)g.cout, (uint64_t)g.ksize};
+  const uint64_t bstr[2] = {128, (uint64_t)g.cout * 128};
+  const uint32_t bbox[3] = {64, (uint32_t)kmajor_b_rows(p, bn_tile), 1};
+  rc = make_tmap(&bmap, packed, 3, bdims, bstr, bbox);
+  if (rc != RIGL_OK) return rc;
+  CUtensorMap omap = bmap;
+  p.tma_store = g_tma_store ? 1 : 0;
+  if (p.tma_store) {
+    rc = make_act_map(&omap, y, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, abox);
+    if (rc != RIGL_OK) return rc;
+  }
+  return dispatch_kmajor(g.cout, amaps, bmap, omap, p, bn_tile, s);
+}
+
+static ConvGeom smallc_as_gemm(const ConvGeom& g) {     // the wgrad work decomposition sees k taps of 64 "channels"
+  ConvGeom v = g;
+  v.ksize = 1; v.cin = 64;
+  return v;
+}
+
+size_t smallc_wgrad_ws_bytes(const ConvGeom& g) {
+  int bw, bh, bn;
+  choose_box(g.out_w, g.out_h, g.batch, 64, &bw, &bh, &bn);
+  ConvGeom v = smallc_as_gemm(g);
+  return wgrad_ws_elems(v, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g)) * g.ksize * sizeof(float) + 256;
+}
+
+int smallc_wgrad(const ConvGeom& g, const void* xp, const void* dy, float* dw, float beta, void* ws, size_t ws_bytes,
+                 cudaStream_t s) {
+  int rc = ensure_driver();
+  if (rc != RIGL_OK) return rc;
+  const SmallCGeom q = smallc_geom(g);
+  WgradParams p = {};
+  choose_box(g.out_w, g.out_h, g.batch, 64, &p.bw, &p.bh, &p.bn);
+  p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
+  p.tiles_w = (p.GW + p.bw - 1) / p.bw; p.tiles_h = (p.GH + p.bh - 1) / p.bh; p.tiles_n = (p.NB + p.bn - 1) / p.bn;
+  p.pblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int bn_tile = wgrad_bn_tile(g);
+  const int out_tiles = g.ksize * ((g.cout + bn_tile - 1) / bn_tile);
+  int splits = (2 * g_num_sms + out_tiles - 1) / out_tiles;
+  if (splits > p.pblocks) splits = p.pblocks;
+  if (splits < 1) splits = 1;
+  p.pblocks_per_split = (p.pblocks + splits - 1) / splits;
+  p.splits = (p.pblocks + p.pblocks_per_split - 1) / p.pblocks_per_split;
+  p.ci = 64; p.co = g.cout;
+  p.m_tiles = 1; p.n_tiles = (g.cout + bn_tile - 1) / bn_tile;
+  const long long n_part = (long long)g.ksize * 64 * g.cout;
+  const size_t need = (size_t)p.splits * n_part * sizeof(float);
+  if (ws == nullptr || ws_bytes < need + 256) {
+    set_error("rigl_smallc_wgrad: workspace %zu < required %zu", ws_bytes, need + 256);
+    return RIGL_ERR_WORKSPACE;
+  }
+  p.out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  p.split_stride = n_part;
+  TMaps4 xmaps;
+  const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  for (int par = 0; par < g.stride; ++par) {
+    rc = make_window_map(&xmaps.a[par], xp, g, q, par, box);
+    if (rc != RIGL_OK) return rc;
+  }
+  for (int i = g.stride; i < 4; ++i) xmaps.a[i] = xmaps.a[0];
+  p.ntaps = g.ksize;
+  for (int kh = 0; kh < g.ksize; ++kh) {
+    TapInfo& t = p.taps[kh];
+    t.map_id = (int8_t)(kh % g.stride); t.dh = (int8_t)(kh / g.stride); t.dw = 0; t.b_tap = kh;
+  }
+  CUtensorMap dymap;
+  rc = make_act_map(&dymap, dy, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, box);
+  if (rc != RIGL_OK) return rc;
+  rc = (bn_tile == 256)   ? launch_wgrad<256, 4>(xmaps, dymap, p, s)
+       : (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s)
+                          : launch_wgrad<64, 8>(xmaps, dymap, p, s);
+  if (rc != RIGL_OK) return rc;
+  const long long total = (long long)g.ksize * g.ksize * g.cin * g.cout;
+  k_smallc_unpack<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g, p.out, p.split_stride, p.splits, dw, beta);
+  RIGL_LAUNCH_CHECK("k_smallc_unpack");
   return RIGL_OK;
 }
 

@@ -178,17 +178,27 @@ class SparseConv2d(_MaskedLayer):
     self._setup(name or 'Conv', (k, k, int(in_channels), int(units)), device, registry,
                 kernel_initializer)
     self.patch_mode = (int(in_channels) % 8 != 0) and k > 1
+    # small-Cin fast path (window tensor maps over a zero-bordered 8-channel copy of the input)
+    self.smallc_mode = self.patch_mode and int(in_channels) <= 8 and k <= 8 and int(units) % 8 == 0 and s in (1, 2)
     if self.patch_mode:
       self._kdim = k * k * int(in_channels)
       self._kpitch = (self._kdim + 7) // 8 * 8
       nbytes = int(_cabi.lib().rigl_packed_weights_bytes(1, self._kdim, self._cout))
       self.packed_patch = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if self.smallc_mode:
+      self.packed_smallc = torch.zeros(k * int(units) * 64 * 2, dtype=torch.uint8, device=device)
+    self._use_smallc = False
 
   def pack(self):
-    if self.patch_mode:
+    if self.patch_mode:      # both stem operand forms are tiny; which one runs is decided per call
       _cabi.check(_cabi.lib().rigl_pack_masked_weights(
           self.weight.data_ptr(), self.mask.bits.data_ptr(), 1, self._kdim, self._cout,
           self.packed_patch.data_ptr(), _cabi.stream_ptr()), 'rigl_pack_masked_weights')
+      if self.smallc_mode:
+        d = self._desc(1, max(self.ksize, 8), max(self.ksize, 8))
+        _cabi.check(_cabi.lib().rigl_smallc_pack_weights(
+            d, self.weight.data_ptr(), self.mask.bits.data_ptr(), self.packed_smallc.data_ptr(),
+            _cabi.stream_ptr()), 'rigl_smallc_pack_weights')
     else:
       super(SparseConv2d, self).pack()
 
@@ -246,6 +256,20 @@ class SparseConv2d(_MaskedLayer):
     y = torch.empty((n, self._cout, d.out_h, d.out_w), dtype=torch.bfloat16, device=x.device,
                     memory_format=torch.channels_last)
     packed, src = self.packed, x
+    self._use_smallc = bool(self.smallc_mode and _cabi.lib().rigl_smallc_supported(d))
+    if self._use_smallc:
+      try:
+        xp = torch.empty(int(_cabi.lib().rigl_smallc_padded_bytes(d)), dtype=torch.uint8, device=x.device)
+        _cabi.check(_cabi.lib().rigl_smallc_pad_input(d, x.data_ptr(), xp.data_ptr(), _cabi.stream_ptr()),
+                    'rigl_smallc_pad_input')
+        _cabi.check(_cabi.lib().rigl_smallc_fprop(d, xp.data_ptr(), self.packed_smallc.data_ptr(), y.data_ptr(),
+                                                  _cabi.stream_ptr()), 'rigl_smallc_fprop')
+        self._patch_cache = xp
+        return y
+      except _cabi.RiglError as e:       # e.g. a driver that rejects the window tensor map
+        if 'cuTensorMapEncodeTiled' not in str(e):
+          raise
+        self.smallc_mode = self._use_smallc = False
     if self.patch_mode:
       self._patch_cache = src = self._patches(x)
       d, packed = self._patch_desc(src.shape[0]), self.packed_patch
@@ -270,6 +294,13 @@ class SparseConv2d(_MaskedLayer):
   def _wgrad(self, x, dy, out, accumulate):
     n, c, h, w = x.shape
     d, src = self._desc(n, h, w), x
+    if self._use_smallc and getattr(self, '_patch_cache', None) is not None:
+      xp, self._patch_cache = self._patch_cache, None
+      ws = _workspace(x.device, _cabi.lib().rigl_smallc_workspace_bytes(d))
+      _cabi.check(_cabi.lib().rigl_smallc_wgrad(
+          d, xp.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
+          ws.numel(), _cabi.stream_ptr()), 'rigl_smallc_wgrad')
+      return
     if self.patch_mode:
       src = self._patch_cache if getattr(self, '_patch_cache', None) is not None else self._patches(x)
       self._patch_cache = None

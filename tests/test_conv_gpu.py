@@ -45,7 +45,9 @@ CONV_CASES = [
     (2, 9, 7, 8, 16, 3, 2, 0.8),
     (3, 8, 8, 64, 64, 1, 1, 0.0),
     (2, 14, 14, 64, 128, 1, 2, 0.4),
-    (2, 12, 12, 3, 8, 7, 2, 0.14),      # stem-like: cin=3 (SIMT path)
+    (2, 12, 12, 3, 8, 7, 2, 0.14),      # stem-like: cin=3 (small-Cin window-map path / SIMT)
+    (3, 32, 32, 3, 64, 7, 2, 0.14),
+    (2, 17, 17, 3, 16, 3, 1, 0.3),
     (4, 16, 16, 64, 64, 3, 1, 0.64),
     (8, 14, 14, 128, 128, 3, 1, 0.82),
     (4, 28, 28, 128, 128, 3, 2, 0.82),
