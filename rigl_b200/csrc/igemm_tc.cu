@@ -552,7 +552,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
-static bool g_cluster_mc = true;    // RIGL_CLUSTER_MC=0 disables the 2-CTA weight-tile multicast
+static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
+                                    // on ResNet-50 b256: the main loops are not L2-bandwidth bound)
 static int g_num_sms = 0;
 static std::once_flag g_once;
 static int g_init_status = RIGL_OK;
@@ -568,7 +569,7 @@ static void init_driver() {
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* e = getenv("RIGL_TMA_STORE")) g_tma_store = !(e[0] == '0');
-  if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -660,7 +661,10 @@ static size_t wgrad_ws_elems(const ConvGeom& g, int* splits_out, int* bps_out, i
 
 // Wider N tiles halve the L2->smem bytes per FLOP (the wgrad main loop is L2-bandwidth bound:
 // K blocks are only 64 pixels deep).
-static int wgrad_bn_tile(const ConvGeom& g) { return g.cout >= 256 ? 256 : (g.cout >= 128 ? 128 : 64); }
+static int wgrad_bn_tile(const ConvGeom& g) {
+  if (g.cout >= 256 && g.cin >= 256) return 256;      // (measured: narrow-Cin layers prefer more, smaller units)
+  return g.cout >= 128 ? 128 : 64;
+}
 
 size_t tc_workspace_bytes(const ConvGeom& g) {
   if (!tc_supported(g, 2)) return 0;
@@ -698,7 +702,11 @@ static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUt
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_kmajor<BN, STAGES, CL>, amaps, bmap, omap, p));
+  if (CL == 1) {
+    k_igemm_kmajor<BN, STAGES, CL><<<cfg.gridDim, cfg.blockDim, smem, s>>>(amaps, bmap, omap, p);
+  } else {
+    RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_kmajor<BN, STAGES, CL>, amaps, bmap, omap, p));
+  }
   RIGL_LAUNCH_CHECK("k_igemm_kmajor");
   return RIGL_OK;
 }
@@ -860,7 +868,11 @@ static int launch_wgrad_cl(const TMaps4& xmaps, const CUtensorMap& dymap, const 
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_wgrad<BN, STAGES, CL>, xmaps, dymap, p));
+  if (CL == 1) {
+    k_igemm_wgrad<BN, STAGES, CL><<<cfg.gridDim, cfg.blockDim, smem, s>>>(xmaps, dymap, p);
+  } else {
+    RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_wgrad<BN, STAGES, CL>, xmaps, dymap, p));
+  }
   RIGL_LAUNCH_CHECK("k_igemm_wgrad");
   return RIGL_OK;
 }

@@ -24,6 +24,7 @@ from . import pruning
 from .masks import MaskVariable
 
 _WS = {}
+STEM_WINDOW_PATH = False     # route small-Cin convs through the window-tensor-map kernels
 
 
 class Profiler(object):
@@ -179,7 +180,10 @@ class SparseConv2d(_MaskedLayer):
                 kernel_initializer)
     self.patch_mode = (int(in_channels) % 8 != 0) and k > 1
     # small-Cin fast path (window tensor maps over a zero-bordered 8-channel copy of the input)
-    self.smallc_mode = self.patch_mode and int(in_channels) <= 8 and k <= 8 and int(units) % 8 == 0 and s in (1, 2)
+    # (measured slower than the patch matrix for the ResNet stem at b256 -- its wgrad re-reads dY
+    # once per filter row -- so it is opt-in: layers.STEM_WINDOW_PATH = True)
+    self.smallc_mode = (STEM_WINDOW_PATH and self.patch_mode and int(in_channels) <= 8 and k <= 8 and
+                        int(units) % 8 == 0 and s in (1, 2))
     if self.patch_mode:
       self._kdim = k * k * int(in_channels)
       self._kpitch = (self._kdim + 7) // 8 * 8

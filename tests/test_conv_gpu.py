@@ -155,3 +155,26 @@ def test_rank_and_channel_errors():
     layer(torch.zeros(2, 8, 4, device=DEV))
   with pytest.raises(ValueError):
     layer(torch.zeros(2, 4, 4, 4, device=DEV))
+
+
+@pytest.mark.parametrize('case', [(2, 12, 12, 3, 8, 7, 2, 0.14), (3, 32, 32, 3, 64, 7, 2, 0.14), (2, 17, 17, 3, 16, 3, 1, 0.3)])
+def test_conv_stem_window_path(case):
+  """The opt-in small-Cin path (zero-bordered 8-channel input + overlapping-window tensor maps)."""
+  from rigl_b200 import layers
+  layers.STEM_WINDOW_PATH = True
+  try:
+    _conv_case(case, force_simt=False)
+  finally:
+    layers.STEM_WINDOW_PATH = False
+
+
+@pytest.mark.parametrize('case', [CONV_CASES[5], CONV_CASES[8], CONV_CASES[10], CONV_CASES[11]])
+def test_conv_cluster_multicast_path(case):
+  """Same results with the 2-CTA multicast clusters (run in a subprocess: the switch is read once)."""
+  import os, subprocess, sys
+  code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_conv_gpu as t; '
+          't._conv_case(%r, False); print("MC_OK")' % (os.path.dirname(os.path.dirname(__file__)),
+                                                       os.path.dirname(__file__), case))
+  env = dict(os.environ, RIGL_CLUSTER_MC='1')
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert 'MC_OK' in out.stdout, out.stdout[-1500:]
