@@ -227,8 +227,63 @@ class TrainHarness(object):
     if self.dp is not None:
       self.dp.attach(model)
 
+  # ---- CUDA-graph mode: the forward+backward and the inner optimizer step are captured once and
+  # replayed (inter-kernel launch gaps and all host work disappear); the data-parallel
+  # all-reduce, the schedule logic and the (rare) mask update stay eager between the replays.
+  def enable_cuda_graph(self, images, labels, warmup=3):
+    """Captures the step for fixed input shapes.  Returns False (and stays eager) if capture fails."""
+    self._sx, self._sy = images.clone(), labels.clone()
+    try:
+      side = torch.cuda.Stream()
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        for _ in range(warmup):
+          self._forward_backward(self._sx, self._sy, set_to_none=False)
+      torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize()
+      self._g_fb = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self._g_fb):
+        self._sloss = self._forward_backward(self._sx, self._sy, set_to_none=False)
+      self._g_opt = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
+        self.inner.step()
+      self.graphed = True
+    except Exception as e:      # stay on the eager path, but say why
+      import warnings
+      warnings.warn('CUDA-graph capture failed, running eagerly: %r' % (e,))
+      torch.cuda.synchronize()
+      self.graphed = False
+    return self.graphed
+
+  def _forward_backward(self, images, labels, set_to_none):
+    for mw in self.model.registry.get_masked_weights():
+      mw.fresh = False
+    self.inner.zero_grad(set_to_none=set_to_none)
+    logits = self.model(images)
+    loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
+    loss.backward()
+    return loss
+
+  def _graphed_step(self, images, labels):
+    self._sx.copy_(images, non_blocking=True)
+    self._sy.copy_(labels, non_blocking=True)
+    self._g_fb.replay()
+    if self.dp is not None:
+      self.dp.reduce_gradients(self.model)
+    self.opt.collect_masked_grads()
+    gs = self.global_step
+    self.opt._global_step = gs
+    # same decision as SparseRigLOptimizerBase.apply_gradients, with the inner step replayed
+    def inner_step():
+      self._g_opt.replay()
+      gs.increment()
+    self.opt.cond_mask_update_op(gs, inner_step)
+    return self._sloss
+
   def step(self, images, labels):
     """images: bf16 [N,3,H,W] channels_last; labels: int64 [N].  Returns the loss tensor."""
+    if getattr(self, 'graphed', False):
+      return self._graphed_step(images, labels)
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
     # without DP the grads are re-created by autograd (no zero-fill, no accumulate pass);
