@@ -44,6 +44,19 @@ def _peaks():
   return 6650.0, 1400.0, 'fallback'
 
 
+def _recorded_traffic():
+  """DRAM bytes per step of the conv kernel family from the committed ncu pass
+  (profiles/r01_dram_traffic_step.json: dram__bytes_read.sum + dram__bytes_write.sum, b256)."""
+  path = os.path.join(ROOT, 'profiles', 'r01_dram_traffic_step.json')
+  try:
+    with open(path) as f:
+      d = json.load(f)
+    return {'dram_bytes_per_step': d['conv_family_dram_bytes_per_step'], 'launches': d['conv_family_launches'],
+            'source': 'profiles/r01_dram_traffic_step.json'}
+  except Exception:
+    return None
+
+
 class ClockSampler(object):
   """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -131,7 +144,7 @@ def run_ours(args):
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
-  launches0 = _cabi.launch_count()
+  launches0 = _cabi.launch_count() + getattr(harness, 'replayed_kernel_launches', 0)
   start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   start.record()
   n_updates = 0
@@ -141,7 +154,7 @@ def run_ours(args):
   stop.record()
   barrier()
   clocks = sampler.stop() if rank == 0 else None
-  launches = _cabi.launch_count() - launches0
+  launches = _cabi.launch_count() + getattr(harness, 'replayed_kernel_launches', 0) - launches0
   ms = torch.tensor([start.elapsed_time(stop)], device=dev, dtype=torch.float64)
   if dist is not None:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -248,7 +261,7 @@ def run_ours(args):
                    'algorithmic_gflop_per_image': ALG_GFLOP_PER_IMAGE,
                    'dense_executed_tflops': DENSE_GFLOP_PER_IMAGE * BATCH / conv_ms,
                    'conv_ms_per_step': conv_ms, 'conv_launches_per_step': n_conv_launch,
-                   'ms_per_step_by_kind': per_kind, 'traffic': None},
+                   'ms_per_step_by_kind': per_kind, 'traffic': _recorded_traffic()},
   }
   if world == 1 and not args.no_cpu_baseline:
     out['cpu_baseline'] = cpu_baseline_leg(sample_batch=args.cpu_batch)

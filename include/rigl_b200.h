@@ -161,6 +161,14 @@ RIGL_API size_t rigl_conv_workspace_bytes(const rigl_conv_desc* d);
 RIGL_API int rigl_masked_conv2d_fprop(const rigl_conv_desc* d, const void* x, const void* packed,
                                       void* y_bf16, float* y_f32, const float* bias, void* ws,
                                       size_t ws_bytes, void* stream);
+/* fprop that also emits the batch-norm statistics of its output from the epilogue
+ * (the BN stats pass over y disappears): bn_partial[rows][2][cout] fp32 receives
+ * per-CTA column sums and sums of squares of the fp32 accumulators, *bn_rows_out (host) the number
+ * of rows written (<= rigl_bn_partial_rows()).  Tensor-core path only (RIGL_ERR_UNSUPPORTED else). */
+RIGL_API int rigl_bn_partial_rows(void);
+RIGL_API int rigl_masked_conv2d_fprop_bnstats(const rigl_conv_desc* d, const void* x, const void* packed,
+                                              void* y_bf16, float* bn_partial, int* bn_rows_out, void* ws,
+                                              size_t ws_bytes, void* stream);
 /* dx = conv^T(dy, mask*W). */
 RIGL_API int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, const void* packed,
                                       void* dx, void* ws, size_t ws_bytes, void* stream);
@@ -206,6 +214,13 @@ RIGL_API int rigl_bn_forward_train(const void* y, const void* residual, const fl
                                    float momentum, int relu, float* running_mean, float* running_var,
                                    float* save_mean, float* save_rstd, float* save_scale,
                                    float* save_shift, void* out, void* ws, size_t ws_bytes, void* stream);
+/* Training forward from conv-epilogue partial sums (rigl_masked_conv2d_fprop_bnstats). */
+RIGL_API int rigl_bn_forward_train_partials(const void* y, const void* residual, const float* gamma,
+                                            const float* beta, const float* partial, int partial_rows,
+                                            int64_t rows, int channels, float eps, float momentum, int relu,
+                                            float* running_mean, float* running_var, float* save_mean,
+                                            float* save_rstd, float* save_scale, float* save_shift, void* out,
+                                            void* stream);
 /* Inference / given statistics: out = [relu](y*scale + shift (+ residual)). */
 RIGL_API int rigl_bn_apply(const void* y, const void* residual, const float* scale, const float* shift,
                            int64_t rows, int channels, int relu, void* out, void* stream);

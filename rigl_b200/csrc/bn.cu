@@ -339,6 +339,33 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
   return RIGL_OK;
 }
 
+// Same as rigl_bn_forward_train but the column sums come from the producing conv's epilogue
+// (partial[rows][2][channels], as written by rigl_masked_conv2d_fprop_bnstats): no stats pass.
+extern "C" int rigl_bn_forward_train_partials(const void* y, const void* residual, const float* gamma,
+                                              const float* beta, const float* partial, int partial_rows,
+                                              int64_t rows, int channels, float eps, float momentum, int relu,
+                                              float* running_mean, float* running_var, float* save_mean,
+                                              float* save_rstd, float* save_scale, float* save_shift, void* out,
+                                              void* stream_) {
+  RIGL_REQUIRE(y && gamma && beta && partial && save_mean && save_rstd && save_scale && save_shift && out,
+               "rigl_bn_forward_train_partials: null argument");
+  RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0 && partial_rows > 0,
+               "rigl_bn_forward_train_partials: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream_;
+  k_bn_finalize_fwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, partial_rows, channels, rows, eps, gamma,
+                                                                  beta, save_mean, save_rstd, save_scale, save_shift,
+                                                                  running_mean, running_var, momentum);
+  RIGL_LAUNCH_CHECK("k_bn_finalize_fwd");
+  const long long nvec = rows * (channels / 8);
+  long long blocks = (nvec + kBnThreads - 1) / kBnThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)residual,
+                                                     save_scale, save_shift, relu, nvec, channels / 8,
+                                                     (__nv_bfloat16*)out);
+  RIGL_LAUNCH_CHECK("k_bn_apply");
+  return RIGL_OK;
+}
+
 extern "C" int rigl_bn_apply(const void* y, const void* residual, const float* scale, const float* shift,
                              int64_t rows, int channels, int relu, void* out, void* stream_) {
   RIGL_REQUIRE(y && scale && shift && out && rows > 0 && channels > 0 && channels % 8 == 0,

@@ -127,6 +127,22 @@ extern "C" int rigl_masked_conv2d_fprop(const rigl_conv_desc* d, const void* x, 
                     (cudaStream_t)stream);
 }
 
+extern "C" int rigl_bn_partial_rows(void) { return tc_max_ctas(); }
+
+extern "C" int rigl_masked_conv2d_fprop_bnstats(const rigl_conv_desc* d, const void* x, const void* packed,
+                                                void* y_bf16, float* bn_partial, int* bn_rows_out, void* ws,
+                                                size_t ws_bytes, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && packed && y_bf16 && bn_partial && bn_rows_out, "rigl_masked_conv2d_fprop_bnstats: null argument");
+  if (force_simt() || !tc_supported(g, 0)) {
+    set_error("rigl_masked_conv2d_fprop_bnstats: shape not on the tensor-core path");
+    return RIGL_ERR_UNSUPPORTED;
+  }
+  return tc_fprop(g, x, packed, y_bf16, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, bn_partial, bn_rows_out);
+}
+
 extern "C" int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, const void* packed,
                                         void* dx, void* ws, size_t ws_bytes, void* stream) {
   ConvGeom g;

@@ -55,7 +55,9 @@ int simt_im2col(const ConvGeom& g, const void* x, void* out, int64_t out_pitch, 
 bool tc_supported(const ConvGeom& g, int which /*0 fprop, 1 dgrad, 2 wgrad*/);
 size_t tc_workspace_bytes(const ConvGeom& g);
 int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, float* y_f32,
-             const float* bias, void* ws, size_t ws_bytes, cudaStream_t s);
+             const float* bias, void* ws, size_t ws_bytes, cudaStream_t s, float* bn_partial = nullptr,
+             int* bn_rows = nullptr);
+int tc_max_ctas();
 int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, void* ws,
              size_t ws_bytes, cudaStream_t s);
 int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, void* ws,

@@ -64,6 +64,7 @@ struct IgemmParams {
   const uint32_t* nnz;              // survivor counts per 64x64 weight tile (or null)
   int nnz_tap_stride, nnz_n_stride, nnz_k_stride;
   int tma_store;                    // 1: epilogue stages bf16 tiles in smem and TMA-stores them
+  float* bn_partial;                // optional [gridDim.x][2][N]: per-CTA column sums / sums of squares of D
 };
 
 struct TMaps4 {
@@ -84,6 +85,32 @@ __device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_
 // ----------------------------------------------------------------------------
 // fprop / dgrad kernel: D[128 pixels, BN] += A[128, 64] * B[BN, 64]^T per (tap, k block)
 // ----------------------------------------------------------------------------
+// Column sums of a 32(rows = lanes) x 32(columns = registers) fp32 block and of its squares by
+// recursive halving: 31 shuffles per statistic instead of 160; lane l ends up owning column l.
+// Rows that lie outside the pixel grid hold exact zeros (their A rows were zero-filled).
+__device__ __forceinline__ void warp_colsum_add(const uint32_t (&r)[32], float* __restrict__ bn_row, int co0, int n,
+                                                int lane) {
+  float v[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); q[j] = v[j] * v[j]; }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float keep_v = upper ? v[j + s] : v[j], send_v = upper ? v[j] : v[j + s];
+      const float keep_q = upper ? q[j + s] : q[j], send_q = upper ? q[j] : q[j + s];
+      v[j] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, s);
+      q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
+    }
+  }
+  const int co = co0 + lane;
+  if (co < n) {
+    atomicAdd(bn_row + co, v[0]);
+    atomicAdd(bn_row + n + co, q[0]);
+  }
+}
+
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs work on the two M tiles of a tile
 // PAIR that share the weight tile: each loads HALF of B and multicasts it into both CTAs'
 // shared memory, which cuts the L2->smem bytes per FLOP by a third (these kernels are bound
@@ -210,6 +237,12 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     const int row = quad * 32 + lane;                     // pixel index inside the box
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t slab_ctr = 0;
+    float* bn_row = p.bn_partial ? p.bn_partial + (size_t)blockIdx.x * 2 * p.N : nullptr;
+    if (bn_row) {            // this CTA's row of the batch-norm partial sums starts at zero
+      for (int i = (warp - 2) * 32 + lane; i < 2 * p.N; i += 128) bn_row[i] = 0.f;
+      __threadfence_block();
+      named_bar_sync(1, 128);
+    }
     for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
       const int n_tile = pair % p.n_tiles;
       const int m_tile = (pair / p.n_tiles) * CL + (int)cta_rank;
@@ -237,6 +270,10 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
           tmem_ld_wait();
+          if (bn_row) {        // fused BN statistics: column sums over this warp's 32 rows, then one RED per column
+            warp_colsum_add(r0, bn_row, co0, p.N, lane);
+            warp_colsum_add(r1, bn_row, co0 + 32, p.N, lane);
+          }
           const uint32_t row_addr = slab + (uint32_t)row * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -635,6 +672,11 @@ static void choose_box(int gw, int gh, int nb, int total, int* bw, int* bh, int*
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static inline int posmod(int a, int b) { return ((a % b) + b) % b; }
 
+int tc_max_ctas() {
+  ensure_driver();
+  return g_num_sms > 0 ? g_num_sms : 148;
+}
+
 bool tc_supported(const ConvGeom& g, int which) {
   if (g.x_pitch % 8 || g.cout % 8) return false;     // 16-byte row pitches for TMA
   if (which == 1 && g.cin % 8) return false;         // dgrad stores 8 channels at a time
@@ -678,6 +720,15 @@ static bool kmajor_use_mc(const IgemmParams& p) {
   return g_cluster_mc && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
 }
 static int kmajor_b_rows(const IgemmParams& p, int bn_tile) { return kmajor_use_mc(p) ? bn_tile / 2 : bn_tile; }
+
+static int kmajor_grid(const IgemmParams& p) {         // CTAs the K-major launcher will use (p.n_tiles set)
+  const int cl = kmajor_use_mc(p) ? 2 : 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pairs = ((m_tiles + cl - 1) / cl) * p.n_tiles;
+  int clusters = g_num_sms / cl;
+  if (pairs < clusters) clusters = pairs;
+  return clusters * cl;
+}
 
 template <int BN, int STAGES, int CL>
 static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap, const IgemmParams& p,
@@ -728,7 +779,7 @@ static int pick_bn(int n_out, long long m_tiles) {
 }
 
 int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, float* y_f32, const float* bias,
-             void* ws, size_t ws_bytes, cudaStream_t s) {
+             void* ws, size_t ws_bytes, cudaStream_t s, float* bn_partial, int* bn_rows) {
   (void)ws; (void)ws_bytes;
   int rc = ensure_driver();
   if (rc != RIGL_OK) return rc;
@@ -774,6 +825,15 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   if (p.tma_store) {
     rc = make_act_map(&omap, y, g.batch, g.out_h, g.out_w, g.cout, g.cout, 1, 0, 0, abox);
     if (rc != RIGL_OK) return rc;
+  }
+  if (bn_partial) {
+    if (!p.tma_store) {
+      set_error("fused BN statistics need the bf16 TMA-store epilogue");
+      return RIGL_ERR_UNSUPPORTED;
+    }
+    p.bn_partial = bn_partial;
+    p.n_tiles = (g.cout + bn_tile - 1) / bn_tile;
+    if (bn_rows) *bn_rows = kmajor_grid(p);
   }
   return dispatch_kmajor(g.cout, amaps, bmap, omap, p, bn_tile, s);
 }

@@ -23,7 +23,19 @@ from . import _cabi
 from . import pruning
 from .masks import MaskVariable
 
+import ctypes as C
+
 _WS = {}
+FUSE_BN_STATS = True          # conv epilogue emits the following BN's batch statistics
+_BN_ROWS = []
+
+
+def _bn_partial_rows():
+  if not _BN_ROWS:
+    _BN_ROWS.append(int(_cabi.lib().rigl_bn_partial_rows()))
+  return _BN_ROWS[0]
+
+
 STEM_WINDOW_PATH = False     # route small-Cin convs through the window-tensor-map kernels
 
 
@@ -192,6 +204,8 @@ class SparseConv2d(_MaskedLayer):
     if self.smallc_mode:
       self.packed_smallc = torch.zeros(k * int(units) * 64 * 2, dtype=torch.uint8, device=device)
     self._use_smallc = False
+    self.collect_bn_stats = False   # set by the model when a FusedBatchNormReLU consumes this output
+    self.bn_partial = None
 
   def pack(self):
     if self.patch_mode:      # both stem operand forms are tiny; which one runs is decided per call
@@ -278,6 +292,19 @@ class SparseConv2d(_MaskedLayer):
       self._patch_cache = src = self._patches(x)
       d, packed = self._patch_desc(src.shape[0]), self.packed_patch
     ws = _workspace(x.device, _cabi.lib().rigl_conv_workspace_bytes(d))
+    self.bn_partial = None
+    if self.collect_bn_stats and self.training and FUSE_BN_STATS:
+      # the epilogue also emits per-CTA column sums / sums of squares of the output (BN statistics)
+      rows = C.c_int(0)
+      part = torch.empty(_bn_partial_rows() * 2 * self._cout, dtype=torch.float32, device=x.device)
+      rc = _cabi.lib().rigl_masked_conv2d_fprop_bnstats(
+          d, src.data_ptr(), packed.data_ptr(), y.data_ptr(), part.data_ptr(), C.byref(rows), ws.data_ptr(),
+          ws.numel(), _cabi.stream_ptr())
+      if rc == 0:
+        self.bn_partial = (part, rows.value, y.data_ptr())
+        return y
+      if rc != -4:        # RIGL_ERR_UNSUPPORTED: fall through to the plain call
+        _cabi.check(rc, 'rigl_masked_conv2d_fprop_bnstats')
     _cabi.check(_cabi.lib().rigl_masked_conv2d_fprop(
         d, src.data_ptr(), packed.data_ptr(), y.data_ptr(), None, None, ws.data_ptr(),
         ws.numel(), _cabi.stream_ptr()), 'rigl_masked_conv2d_fprop')

@@ -20,7 +20,7 @@ def _p(t):
 class _BNFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, y, gamma, beta, residual, mod):
+  def forward(ctx, y, gamma, beta, residual, mod, partial):
     n, c, h, w = y.shape
     rows = n * h * w
     dev = y.device
@@ -29,6 +29,13 @@ class _BNFn(torch.autograd.Function):
     ws = _workspace(dev, _cabi.lib().rigl_bn_workspace_bytes(rows, c) + 8 * c + 256)
 
     def run():
+      if partial is not None:       # statistics already reduced by the producing conv's epilogue
+        _cabi.check(_cabi.lib().rigl_bn_forward_train_partials(
+            y.data_ptr(), _p(residual), gamma.data_ptr(), beta.data_ptr(), partial[0].data_ptr(), partial[1],
+            rows, c, mod.eps, mod.momentum, int(mod.relu), mod.running_mean.data_ptr(),
+            mod.running_var.data_ptr(), save[0].data_ptr(), save[1].data_ptr(), save[2].data_ptr(),
+            save[3].data_ptr(), out.data_ptr(), _cabi.stream_ptr()), 'rigl_bn_forward_train_partials')
+        return
       _cabi.check(_cabi.lib().rigl_bn_forward_train(
           y.data_ptr(), _p(residual), gamma.data_ptr(), beta.data_ptr(), rows, c, mod.eps, mod.momentum,
           int(mod.relu), mod.running_mean.data_ptr(), mod.running_var.data_ptr(), save[0].data_ptr(),
@@ -59,7 +66,7 @@ class _BNFn(torch.autograd.Function):
           save[3].data_ptr(), rows, c, int(mod.relu), dy.data_ptr(), _p(dres), dgb[0].data_ptr(),
           dgb[1].data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr()), 'rigl_bn_backward')
     _timed('bn_bwd', mod, run)
-    return dy, dgb[0], dgb[1], dres, None
+    return dy, dgb[0], dgb[1], dres, None, None
 
 
 class FusedBatchNormReLU(nn.Module):
@@ -77,16 +84,24 @@ class FusedBatchNormReLU(nn.Module):
     self.register_buffer('running_mean', torch.zeros(channels, device=device))
     self.register_buffer('running_var', torch.ones(channels, device=device))
 
-  def forward(self, y, residual=None):
+  def forward(self, y, residual=None, producer=None):
+    """`producer`: the SparseConv2d whose output `y` is; if its epilogue emitted the batch statistics
+    of exactly this tensor (layer.bn_partial), the stats pass is skipped."""
     if y.dim() != 4 or y.shape[1] != self.channels:
       raise ValueError('expected [N,%d,H,W]' % self.channels)
+    partial = None
+    if producer is not None and getattr(producer, 'bn_partial', None) is not None:
+      part, nrows, ptr = producer.bn_partial
+      if ptr == y.data_ptr() and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last):
+        partial = (part, nrows)
+      producer.bn_partial = None
     y = y.contiguous(memory_format=torch.channels_last)
     if y.dtype != torch.bfloat16:
       y = y.to(torch.bfloat16)
     if residual is not None:
       residual = residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     if self.training:
-      return _BNFn.apply(y, self.weight, self.bias, residual, self)
+      return _BNFn.apply(y, self.weight, self.bias, residual, self, partial)
     scale = self.weight.detach() * torch.rsqrt(self.running_var + self.eps)
     shift = self.bias.detach() - self.running_mean * scale
     out = torch.empty_like(y, memory_format=torch.channels_last)

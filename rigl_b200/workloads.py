@@ -46,14 +46,18 @@ class _Bottleneck(nn.Module):
     self.conv2 = mk(filters, filters, 3, strides, 'bottleneck_2_%s' % name)
     self.bn2 = _BNReLU(filters, device=device)
     self.conv3 = mk(filters, 4 * filters, 1, 1, 'bottleneck_3_%s' % name)
+    for conv in (self.proj, self.conv1, self.conv2, self.conv3):
+      if conv is not None:
+        conv.collect_bn_stats = True
     # last BN of the block: zero-init gamma; the residual add + final ReLU are fused into it
     self.bn3 = _BNReLU(4 * filters, relu=True, init_zero=True, device=device)
 
   def forward(self, x):
-    shortcut = x if self.proj is None else self.proj_bn(self.proj(x))
-    y = self.bn1(self.conv1(x))
-    y = self.bn2(self.conv2(y))
-    return self.bn3(self.conv3(y), residual=shortcut)          # relu(BN(conv3) + shortcut)
+    # every conv feeds a BN: its epilogue emits that BN's batch statistics (producer=...)
+    shortcut = x if self.proj is None else self.proj_bn(self.proj(x), producer=self.proj)
+    y = self.bn1(self.conv1(x), producer=self.conv1)
+    y = self.bn2(self.conv2(y), producer=self.conv2)
+    return self.bn3(self.conv3(y), residual=shortcut, producer=self.conv3)   # relu(BN(conv3) + shortcut)
 
 
 class ResNet50(nn.Module):
@@ -67,6 +71,7 @@ class ResNet50(nn.Module):
     self.initial_conv = SparseConv2d(3, 64, 7, strides=2, padding='FIXED', name='resnet_model/initial_conv',
                                      device=device, registry=reg)
     self.initial_bn = _BNReLU(64, device=device)
+    self.initial_conv.collect_bn_stats = True
     blocks = []
     cin = 64
     for g, (filters, n_blocks, stride) in enumerate(((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)), 1):
@@ -82,7 +87,7 @@ class ResNet50(nn.Module):
         kernel_initializer=lambda w: w.normal_(0., .01))      # resnet_model.py:713
 
   def forward(self, x):
-    x = self.initial_bn(self.initial_conv(x))
+    x = self.initial_bn(self.initial_conv(x), producer=self.initial_conv)
     x = max_pool_same(x, 3, 2)                      # 'SAME' 3x3/2 pool, resnet_model.py:636-642
     for blk in self.blocks:
       x = blk(x)
@@ -241,9 +246,13 @@ class TrainHarness(object):
           self._forward_backward(self._sx, self._sy, set_to_none=False)
       torch.cuda.current_stream().wait_stream(side)
       torch.cuda.synchronize()
+      from . import _cabi
       self._g_fb = torch.cuda.CUDAGraph()
+      before = _cabi.launch_count()
       with torch.cuda.graph(self._g_fb):
         self._sloss = self._forward_backward(self._sx, self._sy, set_to_none=False)
+      self.graph_kernel_launches = _cabi.launch_count() - before     # rigl kernels inside one replay
+      self.replayed_kernel_launches = 0
       self._g_opt = torch.cuda.CUDAGraph()
       with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
         self.inner.step()
@@ -268,6 +277,7 @@ class TrainHarness(object):
     self._sx.copy_(images, non_blocking=True)
     self._sy.copy_(labels, non_blocking=True)
     self._g_fb.replay()
+    self.replayed_kernel_launches += self.graph_kernel_launches
     if self.dp is not None:
       self.dp.reduce_gradients(self.model)
     self.opt.collect_masked_grads()

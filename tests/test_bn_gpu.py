@@ -113,3 +113,32 @@ def test_maxpool_same_forward_backward(shape):
   assert float((x.grad.float() - xr.grad).abs().max()) <= 2 ** -7 * float(xr.grad.abs().max()) + 0.0 or \
       float(((x.grad.float() - xr.grad).abs() > 1e-2).float().mean()) < 1e-3
   assert abs(float(x.grad.float().sum()) - float(dy.sum())) <= 1e-2 * float(dy.abs().sum())
+
+
+@pytest.mark.parametrize('case', [(4, 16, 16, 64, 128, 3, 1), (2, 28, 28, 128, 256, 1, 1), (8, 14, 14, 64, 64, 3, 2),
+                                  (3, 32, 32, 3, 64, 7, 2)])
+def test_conv_epilogue_bn_stats_match_stats_pass(case):
+  """BN fed by the conv epilogue's statistics == BN with its own stats pass (fp32 accumulators vs the
+  bf16-rounded tensor: means agree to 2^-9 of the per-channel std, outputs within 2 bf16 ulps)."""
+  from rigl_b200 import layers, pruning
+  n, h, w, cin, cout, k, stride = case
+  torch.manual_seed(cout + k)
+  pruning.reset_default_registry()
+  conv = layers.SparseConv2d(cin, cout, k, strides=stride, padding='FIXED', name='c', device=DEV)
+  conv.mask.assign((torch.rand(k, k, cin, cout, device=DEV) > 0.5).float())
+  conv.collect_bn_stats = True
+  x = torch.randn(n, cin, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  outs = []
+  for fused in (True, False):
+    layers.FUSE_BN_STATS = fused
+    try:
+      bn = FusedBatchNormReLU(cout, relu=True, device=DEV)
+      y = conv(x)
+      assert (conv.bn_partial is not None) == fused
+      outs.append((bn(y, producer=conv).float(), bn.running_mean.clone(), bn.running_var.clone()))
+    finally:
+      layers.FUSE_BN_STATS = True
+  (a, ma, va), (b, mb, vb) = outs
+  assert float((ma - mb).abs().max()) <= 2e-3 * float(vb.sqrt().max()) * 10 + 1e-4
+  assert torch.allclose(va, vb, rtol=5e-3, atol=1e-4)
+  assert float((a - b).abs().max()) <= 2 ** -6 * float(b.abs().max()) + 1e-3
