@@ -199,6 +199,9 @@ def run_ours(args):
   # data-parallel all-reduce is collective; only rank 0 records) ----
   prof_steps = 3
   harness.graphed = False                    # the per-call event timing needs the eager path
+  for _ in range(2):                         # re-warm the eager allocator state after graph replay
+    harness.step(images, labels)
+  barrier()
   if rank == 0:
     Profiler.start()
   for _ in range(prof_steps):
