@@ -88,8 +88,7 @@ __device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_
 // Column sums of a 32(rows = lanes) x 32(columns = registers) fp32 block and of its squares by
 // recursive halving: 31 shuffles per statistic instead of 160; lane l ends up owning column l.
 __device__ __forceinline__ void warp_colsum_add(const uint32_t (&r)[32], float* __restrict__ bn_row, int co0, int n,
-                                                int lane, bool row_valid, float* out_v = nullptr,
-                                                float* out_q = nullptr) {
+                                                int lane, bool row_valid) {
   // rows outside the pixel grid are NOT zero in general (their receptive field can still touch
   // valid input), so they are masked here; the TMA store clips them independently.
   float v[32], q[32];
@@ -105,11 +104,6 @@ __device__ __forceinline__ void warp_colsum_add(const uint32_t (&r)[32], float* 
       v[j] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, s);
       q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
     }
-  }
-  if (bn_row == nullptr) {          // caller accumulates in registers
-    *out_v += v[0];
-    *out_q += q[0];
-    return;
   }
   const int co = co0 + lane;
   if (co < n) {
@@ -245,12 +239,8 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t slab_ctr = 0;
     float* bn_row = p.bn_partial ? p.bn_partial + (size_t)blockIdx.x * 2 * p.N : nullptr;
-    // With one N tile every tile of this CTA covers the same channels: the statistics stay in
-    // registers (lane l of each warp owns column 32*chunk + l) and are flushed once at the end.
-    const bool bn_in_regs = bn_row != nullptr && p.n_tiles == 1;
-    float bn_acc_v[BN / 32], bn_acc_q[BN / 32];
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) { bn_acc_v[i] = 0.f; bn_acc_q[i] = 0.f; }
+    // (keeping the sums in registers across tiles needs the slab loop fully unrolled: measured
+    //  slower -- 255 registers, 2 ms more fprop time per step -- than one RED per column per tile)
     if (bn_row) {            // this CTA's row of the batch-norm partial sums starts at zero
       for (int i = (warp - 2) * 32 + lane; i < 2 * p.N; i += 128) bn_row[i] = 0.f;
       __threadfence_block();
@@ -272,7 +262,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
       if (p.tma_store) {
         // ---- stage 64-channel slabs in smem (128B-swizzled rows) and TMA-store them ----
         const bool issuer = (warp == 2 && lane == 0);
-#pragma unroll
+#pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64) {
           const int co0 = n_tile * BN + c0;
           if (co0 >= p.N) break;                                   // uniform: whole slab out of range
@@ -283,10 +273,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
           tmem_ld_wait();
-          if (bn_in_regs) {    // fused BN statistics kept in registers across tiles
-            warp_colsum_add(r0, nullptr, co0, p.N, lane, pix_ok, &bn_acc_v[c0 / 32], &bn_acc_q[c0 / 32]);
-            warp_colsum_add(r1, nullptr, co0 + 32, p.N, lane, pix_ok, &bn_acc_v[c0 / 32 + 1], &bn_acc_q[c0 / 32 + 1]);
-          } else if (bn_row) { // column sums over this warp's 32 rows, then one RED per column
+          if (bn_row) {        // fused BN statistics: column sums over this warp's 32 rows, one RED per column
             warp_colsum_add(r0, bn_row, co0, p.N, lane, pix_ok);
             warp_colsum_add(r1, bn_row, co0 + 32, p.N, lane, pix_ok);
           }
@@ -374,16 +361,6 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-    if (bn_in_regs) {
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int co = 32 * i + lane;
-        if (co < p.N) {
-          atomicAdd(bn_row + co, bn_acc_v[i]);
-          atomicAdd(bn_row + p.N + co, bn_acc_q[i]);
-        }
-      }
     }
     if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();   // smem must outlive the bulk stores
   }
