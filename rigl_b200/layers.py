@@ -26,7 +26,8 @@ from .masks import MaskVariable
 import ctypes as C
 
 _WS = {}
-FUSE_BN_STATS = True          # conv epilogue emits the following BN's batch statistics
+FUSE_BN_STATS = False         # opt-in: the conv epilogue emits the following BN's batch statistics
+                              # (measured on R50 b256: the epilogue work costs what the stats pass saves)
 _BN_ROWS = []
 
 

@@ -137,7 +137,7 @@ def test_conv_epilogue_bn_stats_match_stats_pass(case):
       assert (conv.bn_partial is not None) == fused
       outs.append((bn(y, producer=conv).float(), bn.running_mean.clone(), bn.running_var.clone()))
     finally:
-      layers.FUSE_BN_STATS = True
+      layers.FUSE_BN_STATS = False
   (a, ma, va), (b, mb, vb) = outs
   assert float((ma - mb).abs().max()) <= 2e-3 * float(vb.sqrt().max()) * 10 + 1e-4
   assert torch.allclose(va, vb, rtol=5e-3, atol=1e-4)
