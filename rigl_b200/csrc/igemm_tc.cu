@@ -388,6 +388,219 @@ struct WgradParams {
   long long split_stride;           // elements between split slices
 };
 
+// ----------------------------------------------------------------------------
+// CTA-pair version of the fprop / dgrad kernel: tcgen05.mma.cta_group::2, M = 256.
+// A single SM cannot feed its tensor core from shared memory at full rate with a 128 x N x 64
+// tile (per K block it writes A+B once and reads them once: ~190 B/clk against a 128 B/clk smem
+// port).  With cta_group::2 the two SMs of a TPC compute ONE 256 x N tile: each holds its own
+// 128 pixel rows of A and only HALF of the weight tile, so the per-SM smem traffic per FLOP drops
+// by a third and the instruction count halves.  Protocol (as CUTLASS / the Blackwell guide):
+//   * both CTAs' TMA loads (.cta_group::2) complete on the LEADER's full barrier
+//     (count 2: leader's arrive.expect_tx for both halves + the peer's remote arrive);
+//   * only the leader issues MMAs; tcgen05.commit.cta_group::2 multicasts the "slot free" and
+//     "accumulator ready" arrivals to both CTAs;
+//   * each CTA's epilogue drains its own 128 TMEM lanes and arrives on the leader's
+//     "accumulator free" barrier (count 8).
+// ----------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUtensorMap bmap,
+                const __grid_constant__ CUtensorMap omap, const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = kBM * kBK * 2;              // my 128 pixel rows: 16 KB
+  constexpr uint32_t kBBytes = (BN / 2) * kBK * 2;          // my half of the weight tile
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(2 * kBM, BN, 0, 0);
+  constexpr uint32_t kSlabBytes = kBM * 64 * 2;
+  constexpr uint16_t kPairMask = 0x3;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_base = smem_base + STAGES * kStageBytes;
+  const uint32_t bar_base = out_base + 2 * kSlabBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
+    prefetch_tmap(&bmap);
+    if (p.tma_store) prefetch_tmap(&omap);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_pairs = m_pairs * p.n_tiles;
+  const int cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
+  constexpr int kBN64 = (BN + 63) / 64;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+        const int n_tile = pair % p.n_tiles;
+        const int m_tile = (pair / p.n_tiles) * 2 + (int)cta_rank;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        bool first = true;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const TapInfo tap = p.taps[t];
+          for (int kb = 0; kb < p.kblks; ++kb) {
+            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
+            first = false;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * kStageBytes;
+            const uint32_t b_dst = a_dst + kABytes;
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes land here
+            else mbar_arrive_leader(full_bar(stage));
+            tma_load_4d_2cta(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                             th * p.bh + tap.dh, tn * p.bn);
+            tma_load_3d_2cta(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2),
+                             tap.b_tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+        const int n_tile = pair % p.n_tiles;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        bool first = true;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int kb = 0; kb < p.kblks; ++kb) {
+            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + stage * kStageBytes;
+            const uint32_t b_src = a_src + kABytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_src + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc(b_src + k * 32, 16, 1024);
+              umma_bf16_2cta(d_tmem, da, db, kIdesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit_2cta_mc(empty_bar(stage), kPairMask);     // slot free in BOTH CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit_2cta_mc(tfull_bar(acc), kPairMask);           // accumulator ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t slab_ctr = 0;
+    for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+      const int n_tile = pair % p.n_tiles;
+      const int m_tile = (pair / p.n_tiles) * 2 + (int)cta_rank;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int pw = tw * p.bw + row % p.bw;
+      const int ph = th * p.bh + (row / p.bw) % p.bh;
+      const int pn = tn * p.bn + row / (p.bw * p.bh);
+      const bool pix_ok = pw < p.GW && ph < p.GH && pn < p.NB;
+      const long long o_pix = p.o_off + pn * p.o_sn + ph * p.o_sh + pw * p.o_sw;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const bool issuer = (warp == 2 && lane == 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int co0 = n_tile * BN + c0;
+        if (co0 >= p.N) break;
+        uint32_t r0[32], r1[32];
+        if (p.tma_store) {
+          const uint32_t slab = out_base + (uint32_t)(slab_ctr & 1) * kSlabBytes;
+          if (issuer) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
+          tmem_ld_wait();
+          const uint32_t row_addr = slab + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = 8 * j + 2 * q;
+              const float a = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
+              const float b = __uint_as_float(e + 1 < 32 ? r0[e + 1] : r1[e + 1 - 32]);
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint32_t dst = row_addr + (uint32_t)((j ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        } else {
+          // direct global stores (fp32 output / bias: the dense layer)
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
+          tmem_ld_wait();
+          if (pix_ok) {
+            for (int j = 0; j < 64 && co0 + j < p.N; ++j) {
+              float a = __uint_as_float(j < 32 ? r0[j & 31] : r1[j & 31]);
+              if (p.bias) a += __ldg(p.bias + co0 + j);
+              if (p.out_bf16) p.out_bf16[o_pix + co0 + j] = __float2bfloat16(a);
+              if (p.out_f32) p.out_f32[o_pix + co0 + j] = a;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_leader(tempty_bar(acc));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (p.tma_store && warp == 2 && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
 // CL = CTAs per cluster (1 or 2).  The dY tile depends only on (pixel block, N tile), so with
 // CL == 2 two work units that differ in (tap, M tile) share it: each CTA fetches half of the dY
 // boxes and multicasts them to both (same protocol as k_igemm_kmajor).
@@ -592,6 +805,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
+static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
 static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
                                     // on ResNet-50 b256: the main loops are not L2-bandwidth bound)
 static int g_num_sms = 0;
@@ -610,6 +824,7 @@ static void init_driver() {
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* e = getenv("RIGL_TMA_STORE")) g_tma_store = !(e[0] == '0');
   if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
+  if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -719,10 +934,15 @@ size_t tc_workspace_bytes(const ConvGeom& g) {
 }
 
 // With the 2-CTA multicast each CTA fetches half of the weight tile (B box = bn_tile/2 rows).
-static bool kmajor_use_mc(const IgemmParams& p) {
-  return g_cluster_mc && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
+static bool kmajor_use_pair(const IgemmParams& p) {      // CTA-pair (cta_group::2) kernel
+  return g_cta_pair && p.bn_partial == nullptr && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
 }
-static int kmajor_b_rows(const IgemmParams& p, int bn_tile) { return kmajor_use_mc(p) ? bn_tile / 2 : bn_tile; }
+static bool kmajor_use_mc(const IgemmParams& p) {
+  return !kmajor_use_pair(p) && g_cluster_mc && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
+}
+static int kmajor_b_rows(const IgemmParams& p, int bn_tile) {
+  return (kmajor_use_mc(p) || kmajor_use_pair(p)) ? bn_tile / 2 : bn_tile;
+}
 
 static int kmajor_grid(const IgemmParams& p) {         // CTAs the K-major launcher will use (p.n_tiles set)
   const int cl = kmajor_use_mc(p) ? 2 : 1;
@@ -765,9 +985,42 @@ static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUt
   return RIGL_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_kmajor2(const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap, const IgemmParams& p,
+                          cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + (BN / 2) * kBK * 2) + 2 * (kBM * 64 * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor2<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+  int clusters = g_num_sms / 2;
+  if (pairs < clusters) clusters = pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RIGL_CUDA(cudaLaunchKernelEx(&cfg, k_igemm_kmajor2<BN, STAGES>, amaps, bmap, omap, p));
+  RIGL_LAUNCH_CHECK("k_igemm_kmajor2");
+  return RIGL_OK;
+}
+
 static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap,
                            IgemmParams& p, int bn_tile, cudaStream_t s) {
   p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
+  if (kmajor_use_pair(p)) {               // CTA-pair MMA (M = 256); bmap was built with bn_tile/2 rows
+    if (bn_tile == 64) return launch_kmajor2<64, 8>(amaps, bmap, omap, p, s);
+    if (bn_tile == 128) return launch_kmajor2<128, 6>(amaps, bmap, omap, p, s);
+    return launch_kmajor2<256, 5>(amaps, bmap, omap, p, s);
+  }
   const bool mc = kmajor_use_mc(p);                        // multicast needs a partner M tile
   if (bn_tile == 64) return mc ? launch_kmajor<64, 8, 2>(amaps, bmap, omap, p, s) : launch_kmajor<64, 8, 1>(amaps, bmap, omap, p, s);
   if (bn_tile == 128) return mc ? launch_kmajor<128, 6, 2>(amaps, bmap, omap, p, s) : launch_kmajor<128, 6, 1>(amaps, bmap, omap, p, s);
@@ -798,6 +1051,7 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   p.o_off = 0; p.o_sw = g.cout; p.o_sh = (long long)g.out_w * g.cout; p.o_sn = (long long)g.out_h * g.out_w * g.cout;
   p.nnz = reinterpret_cast<const uint32_t*>(pk + L.off_nnz);
   p.nnz_tap_stride = L.n_tiles * L.k_tiles; p.nnz_n_stride = L.k_tiles; p.nnz_k_stride = 1;
+  p.bn_partial = bn_partial;            // (decides the kernel variant, hence the B box: set before the maps)
   TMaps4 amaps;
   const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
   bool made[4] = {false, false, false, false};

@@ -175,6 +175,19 @@ def test_conv_cluster_multicast_path(case):
   code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_conv_gpu as t; '
           't._conv_case(%r, False); print("MC_OK")' % (os.path.dirname(os.path.dirname(__file__)),
                                                        os.path.dirname(__file__), case))
-  env = dict(os.environ, RIGL_CLUSTER_MC='1')
+  env = dict(os.environ, RIGL_CLUSTER_MC='1', RIGL_CTA_PAIR='0')
   out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   assert 'MC_OK' in out.stdout, out.stdout[-1500:]
+
+
+@pytest.mark.parametrize('case', [CONV_CASES[0], CONV_CASES[5], CONV_CASES[7], CONV_CASES[9], CONV_CASES[12]])
+def test_conv_single_cta_mma_path(case):
+  """The default K-major kernel is the CTA-pair one (cta_group::2); this keeps the single-CTA
+  (M = 128) kernel covered."""
+  import os, subprocess, sys
+  code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_conv_gpu as t; '
+          't._conv_case(%r, False); print("ONE_OK")' % (os.path.dirname(os.path.dirname(__file__)),
+                                                        os.path.dirname(__file__), case))
+  env = dict(os.environ, RIGL_CTA_PAIR='0')
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert 'ONE_OK' in out.stdout, out.stdout[-1500:]
