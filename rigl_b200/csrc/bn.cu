@@ -145,11 +145,24 @@ __device__ __forceinline__ void slab_sums(const float* __restrict__ partial, int
                                           double* s_out, double* q_out) {
   __shared__ double sm_s[32][33], sm_q[32][33];
   double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int b = threadIdx.y; b < nblocks; b += 32) {
+  if (c < C) {
+    // 8 rows (16 independent loads) in flight per thread: the loop is L2-latency bound, not bandwidth bound.
+    int b = threadIdx.y;
+    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+      float vs[8], vq[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        vs[u] = __ldg(partial + (size_t)(b + u * 32) * 2 * C + c);
+        vq[u] = __ldg(partial + (size_t)(b + u * 32) * 2 * C + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += (double)vs[u]; q += (double)vq[u]; }
+    }
+    for (; b < nblocks; b += 32) {
       s += (double)partial[(size_t)b * 2 * C + c];
       q += (double)partial[(size_t)b * 2 * C + C + c];
     }
+  }
   sm_s[threadIdx.y][threadIdx.x] = s;
   sm_q[threadIdx.y][threadIdx.x] = q;
   __syncthreads();

@@ -532,15 +532,15 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const bool issuer = (warp == 2 && lane == 0);
+      if (p.tma_store) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
-        const int co0 = n_tile * BN + c0;
-        if (co0 >= p.N) break;
-        uint32_t r0[32], r1[32];
-        if (p.tma_store) {
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int co0 = n_tile * BN + c0;
+          if (co0 >= p.N) break;
           const uint32_t slab = out_base + (uint32_t)(slab_ctr & 1) * kSlabBytes;
           if (issuer) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
+          uint32_t r0[32], r1[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
           tmem_ld_wait();
@@ -568,17 +568,24 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
             tma_store_commit();
           }
           ++slab_ctr;
-        } else {
-          // direct global stores (fp32 output / bias: the dense layer)
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
+        }
+      } else {
+        // direct global stores (fp32 output / bias: the dense layer); static register indexing only
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r);
           tmem_ld_wait();
-          if (pix_ok) {
-            for (int j = 0; j < 64 && co0 + j < p.N; ++j) {
-              float a = __uint_as_float(j < 32 ? r0[j & 31] : r1[j & 31]);
-              if (p.bias) a += __ldg(p.bias + co0 + j);
-              if (p.out_bf16) p.out_bf16[o_pix + co0 + j] = __float2bfloat16(a);
-              if (p.out_f32) p.out_f32[o_pix + co0 + j] = a;
+          const int co0 = n_tile * BN + c0;
+          if (pix_ok && co0 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (co0 + j < p.N) {
+                float a = __uint_as_float(r[j]);
+                if (p.bias) a += __ldg(p.bias + co0 + j);
+                if (p.out_bf16) p.out_bf16[o_pix + co0 + j] = __float2bfloat16(a);
+                if (p.out_f32) p.out_f32[o_pix + co0 + j] = a;
+              }
             }
           }
         }
@@ -806,6 +813,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
+static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
 static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
                                     // on ResNet-50 b256: the main loops are not L2-bandwidth bound)
 static int g_num_sms = 0;
@@ -825,6 +833,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_TMA_STORE")) g_tma_store = !(e[0] == '0');
   if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -926,11 +935,16 @@ static int wgrad_bn_tile(const ConvGeom& g) {
   return g.cout >= 128 ? 128 : 64;
 }
 
+#include "halo3x3.cuh"
+
 size_t tc_workspace_bytes(const ConvGeom& g) {
   if (!tc_supported(g, 2)) return 0;
   int bw, bh, bn;
   choose_box(g.out_w, g.out_h, g.batch, 64, &bw, &bh, &bn);
-  return wgrad_ws_elems(g, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g)) * sizeof(float) + 256;
+  size_t elems = wgrad_ws_elems(g, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g));
+  HaloParams hp;
+  if (halo_wgrad_ok(g, &hp)) { const size_t e = halo_wgrad_ws_elems(g, hp); if (e > elems) elems = e; }
+  return elems * sizeof(float) + 256;
 }
 
 // With the 2-CTA multicast each CTA fetches half of the weight tile (B box = bn_tile/2 rows).
@@ -1041,6 +1055,11 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   if (rc != RIGL_OK) return rc;
   const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  {
+    HaloParams hp = {};
+    if (y != nullptr && y_f32 == nullptr && bias == nullptr && bn_partial == nullptr && halo_fprop_ok(g, &hp))
+      return halo_launch_kmajor(hp, x, g.cin, g.x_pitch, pk + L.off_fprop, L.cin_pad, g.cout, y, g.cout, false, s);
+  }
   IgemmParams p = {};
   choose_box(g.out_w, g.out_h, g.batch, 128, &p.bw, &p.bh, &p.bn);
   p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
@@ -1103,6 +1122,11 @@ int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, vo
   const PackedLayout L = packed_layout(g.taps(), g.cin, g.cout);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   const int st = g.stride;
+  {
+    HaloParams hp = {};
+    if (halo_dgrad_ok(g, &hp))
+      return halo_launch_kmajor(hp, dy, g.cout, g.cout, pk + L.off_dgrad, L.cout_pad, g.cin, dx, g.x_pitch, true, s);
+  }
   // classes of input pixels by parity; each class is one launch over its sub-grid
   bool need_zero = false;
   for (int ph = 0; ph < st && !need_zero; ++ph)
@@ -1206,6 +1230,24 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
              cudaStream_t s) {
   int rc = ensure_driver();
   if (rc != RIGL_OK) return rc;
+  {
+    HaloParams hp = {};
+    if (halo_wgrad_ok(g, &hp)) {
+      const size_t need = halo_wgrad_ws_elems(g, hp) * sizeof(float);
+      float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+      if (ws == nullptr || ws_bytes < need + 256) {
+        set_error("rigl_conv2d_wgrad_dense: workspace %zu < required %zu", ws_bytes, need + 256);
+        return RIGL_ERR_WORKSPACE;
+      }
+      rc = halo_launch_wgrad(hp, g, x, dy, wsf, s);
+      if (rc != RIGL_OK) return rc;
+      const long long n_w9 = (long long)9 * g.cin * g.cout;
+      const long long threads = (n_w9 + 3) / 4;
+      k_splitk_reduce<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(wsf, n_w9, halo_wgrad_grid(hp), dw, n_w9, beta);
+      RIGL_LAUNCH_CHECK("k_splitk_reduce");
+      return RIGL_OK;
+    }
+  }
   WgradParams p = {};
   choose_box(g.out_w, g.out_h, g.batch, 64, &p.bw, &p.bh, &p.bn);
   p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;

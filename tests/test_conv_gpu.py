@@ -180,6 +180,36 @@ def test_conv_cluster_multicast_path(case):
   assert 'MC_OK' in out.stdout, out.stdout[-1500:]
 
 
+# 3x3 / stride 1 / pad 1 layers with <= 64 reduction channels run on the halo kernels (one halo tile in
+# shared memory feeds all nine taps): full and partial channel blocks, H not a multiple of the strip,
+# H smaller than a strip, several N tiles, every halo pitch (16 / 32 / 64).
+HALO_CASES = [
+    (2, 14, 14, 64, 64, 3, 1, 0.6),
+    (3, 56, 56, 64, 64, 3, 1, 0.64),
+    (2, 28, 28, 32, 128, 3, 1, 0.8),
+    (2, 13, 27, 64, 24, 3, 1, 0.5),
+    (5, 6, 14, 16, 64, 3, 1, 0.3),
+    (2, 28, 28, 64, 64, 3, 1, 0.9, 'SAME'),
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES)
+def test_conv_halo_path(case):
+  _conv_case(case, force_simt=False)
+
+
+@pytest.mark.parametrize('case', [HALO_CASES[1], HALO_CASES[3]])
+def test_conv_halo_disabled_matches(case):
+  """RIGL_HALO3X3=0 routes the same layers through the generic per-tap kernels."""
+  import os, subprocess, sys
+  code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_conv_gpu as t; '
+          't._conv_case(%r, False); print("GEN_OK")' % (os.path.dirname(os.path.dirname(__file__)),
+                                                        os.path.dirname(__file__), case))
+  env = dict(os.environ, RIGL_HALO3X3='0')
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert 'GEN_OK' in out.stdout, out.stdout[-1500:]
+
+
 @pytest.mark.parametrize('case', [CONV_CASES[0], CONV_CASES[5], CONV_CASES[7], CONV_CASES[9], CONV_CASES[12]])
 def test_conv_single_cta_mma_path(case):
   """The default K-major kernel is the CTA-pair one (cta_group::2); this keeps the single-CTA

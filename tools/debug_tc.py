@@ -37,6 +37,10 @@ SMALL = [
     (4, 56, 56, 64, 256, 1, 1, 0.0),
     (4, 56, 56, 256, 64, 1, 1, 0.0),
     (2, 32, 32, 3, 64, 7, 2, 0.14),
+    (2, 14, 14, 64, 64, 3, 1, 0.6),
+    (2, 28, 28, 32, 128, 3, 1, 0.8),
+    (2, 13, 27, 64, 24, 3, 1, 0.5),
+    (5, 6, 14, 16, 64, 3, 1, 0.3),
 ]
 BIG = [
     (32, 56, 56, 64, 64, 3, 1, 0.64),
