@@ -25,6 +25,7 @@ struct HaloParams {
   int Wp;                       // halo row pitch in pixels: power of two, W + 2 <= Wp <= 128
   int R;                        // output rows per strip (multiple of 128 / Wp)
   int T;                        // 128-position M tiles per strip (R * Wp / 128)
+  int nbuf;                     // halo tiles in flight (2..4)
   int strips_per_image, total_strips;
   int N;                        // fprop/dgrad: output channels.  wgrad: co
   int ci;                       // wgrad: input channels (<= 64)
@@ -48,15 +49,15 @@ k_halo3x3_kmajor(const __grid_constant__ CUtensorMap amap, const __grid_constant
   constexpr uint32_t kIdesc = make_idesc_bf16(128, 64, 0, 0);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base;                                   // 9 taps x 8 KB
-  const uint32_t a_base = b_base + 9 * kHaloBTapBytes;                 // 2 halo tiles
-  const uint32_t out_base = a_base + 2 * p.a_buf_bytes;                // 2 staging slabs
+  const uint32_t a_base = b_base + 9 * kHaloBTapBytes;                 // nbuf halo tiles
+  const uint32_t out_base = a_base + p.nbuf * p.a_buf_bytes;           // 2 staging slabs
   const uint32_t bar_base = out_base + 2 * kHaloSlabBytes;
   const uint32_t b_full = bar_base;
   auto a_full = [&](int b) { return bar_base + 8u * (1 + b); };
-  auto a_empty = [&](int b) { return bar_base + 8u * (3 + b); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (5 + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (7 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * 9;
+  auto a_empty = [&](int b) { return bar_base + 8u * (5 + b); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (9 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (11 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 13;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,7 +65,7 @@ k_halo3x3_kmajor(const __grid_constant__ CUtensorMap amap, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&amap); prefetch_tmap(&bmap); prefetch_tmap(&omap);
     mbar_init(b_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(a_full(b), 1); mbar_init(a_empty(b), 1); }
+    for (int b = 0; b < p.nbuf; ++b) { mbar_init(a_full(b), 1); mbar_init(a_empty(b), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
   }
@@ -85,37 +86,39 @@ k_halo3x3_kmajor(const __grid_constant__ CUtensorMap amap, const __grid_constant
         mbar_wait(a_empty(buf), phase ^ 1u);
         mbar_arrive_expect_tx(a_full(buf), p.a_tx_bytes);
         tma_load_4d(a_base + buf * p.a_buf_bytes, &amap, a_full(buf), 0, -1, h0 - 1, n);
-        if (++buf == 2) { buf = 0; phase ^= 1u; }
+        if (++buf == p.nbuf) { buf = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(b_full, 0);
-      int buf = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
-        mbar_wait(a_full(buf), phase);
+    // The whole warp runs the loop converged; one elected lane issues (see ptx::elect_one).
+    mbar_wait(b_full, 0);
+    int buf = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint64_t b_desc0 = make_smem_desc(b_base, 16, 1024);
+    for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+      mbar_wait(a_full(buf), phase);
+      tc_fence_after();
+      const uint64_t a_desc0 = make_smem_desc(a_base + buf * p.a_buf_bytes, 16, 1024);
+      for (int t = 0; t < p.T; ++t) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t a_buf = a_base + buf * p.a_buf_bytes;
-        for (int t = 0; t < p.T; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+        if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {              // (unrolled: static indices into the param arrays)
-            const uint32_t a_src = a_buf + (uint32_t)(t * 128 + p.row_off[tap]) * 128u;
-            const uint32_t b_src = b_base + (uint32_t)tap * kHaloBTapBytes;
+          for (int tap = 0; tap < 9; ++tap) {              // descriptor start addresses are in 16-byte units
+            const uint64_t da = a_desc0 + (uint64_t)((t * 128 + p.row_off[tap]) * 8);
+            const uint64_t db = b_desc0 + (uint64_t)(tap * (kHaloBTapBytes >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, make_smem_desc(a_src + k * 32, 16, 1024), make_smem_desc(b_src + k * 32, 16, 1024),
-                        kIdesc, (tap == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (tap == 0 && k == 0) ? 0u : 1u);
           }
           umma_commit(tfull_bar(acc));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        umma_commit(a_empty(buf));                         // halo tile reusable once its MMAs retire
-        if (++buf == 2) { buf = 0; phase ^= 1u; }
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(a_empty(buf));          // halo tile reusable once its MMAs retire
+      __syncwarp();
+      if (++buf == p.nbuf) { buf = 0; phase ^= 1u; }
     }
   } else {
     const int quad = warp & 3;
@@ -189,17 +192,17 @@ k_halo3x3_wgrad(const __grid_constant__ CUtensorMap xmap, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t dy_bytes = (uint32_t)(p.R * p.Wp) * 128u;
   const uint32_t stage_bytes = p.a_buf_bytes + dy_bytes;               // [x halo | dy]
-  const uint32_t bar_base = smem_base + 2 * stage_bytes;
+  const uint32_t bar_base = smem_base + p.nbuf * stage_bytes;
   auto full_bar = [&](int b) { return bar_base + 8u * b; };
-  auto empty_bar = [&](int b) { return bar_base + 8u * (2 + b); };
-  const uint32_t tfull = bar_base + 8u * 4;
-  const uint32_t tmem_slot = bar_base + 8u * 5;
+  auto empty_bar = [&](int b) { return bar_base + 8u * (4 + b); };
+  const uint32_t tfull = bar_base + 8u * 8;
+  const uint32_t tmem_slot = bar_base + 8u * 9;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&xmap); prefetch_tmap(&dymap);
-    for (int b = 0; b < 2; ++b) { mbar_init(full_bar(b), 1); mbar_init(empty_bar(b), 1); }
+    for (int b = 0; b < p.nbuf; ++b) { mbar_init(full_bar(b), 1); mbar_init(empty_bar(b), 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -208,7 +211,7 @@ k_halo3x3_wgrad(const __grid_constant__ CUtensorMap xmap, const __grid_constant_
   {
     const uint32_t halo_rows_bytes = p.a_tx_bytes;
     const uint32_t slack = p.a_buf_bytes - halo_rows_bytes;
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < p.nbuf; ++b)
       for (uint32_t i = threadIdx.x * 16u; i < slack; i += kThreads * 16u)
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + b * stage_bytes + halo_rows_bytes + i), "r"(0u)
                      : "memory");
@@ -229,37 +232,42 @@ k_halo3x3_wgrad(const __grid_constant__ CUtensorMap xmap, const __grid_constant_
         const uint32_t x_dst = smem_base + buf * stage_bytes;
         tma_load_4d(x_dst, &xmap, full_bar(buf), 0, -1, h0 - 1, n);
         tma_load_4d(x_dst + p.a_buf_bytes, &dymap, full_bar(buf), 0, 0, h0, n);
-        if (++buf == 2) { buf = 0; phase ^= 1u; }
+        if (++buf == p.nbuf) { buf = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int buf = 0; uint32_t phase = 0;
-      bool first = true;
-      const int ksteps = p.R * p.Wp / 16;
-      for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
-        mbar_wait(full_bar(buf), phase);
-        tc_fence_after();
+    int buf = 0; uint32_t phase = 0;                       // converged warp, one elected lane issues
+    bool first = true;
+    const int ksteps = p.R * p.Wp / 16;
+    for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+      mbar_wait(full_bar(buf), phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t x_src = smem_base + buf * stage_bytes;
-        const uint32_t dy_src = x_src + p.a_buf_bytes;
-#pragma unroll 1
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t db = make_smem_desc(dy_src + (uint32_t)k * 16u * 128u, 8192, 1024);
+        const uint64_t db0 = make_smem_desc(x_src + p.a_buf_bytes, 8192, 1024);
+        uint64_t da0[5];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            // accumulator j holds taps (2j, 2j+1); the last one pairs (7, 8): tap 7 is computed twice
-            const int t0 = j < 4 ? 2 * j : 7, t1 = t0 + 1;
-            const uint32_t a0 = x_src + (uint32_t)(p.row_off[t0] + k * 16) * 128u;
-            const uint32_t lbo = (uint32_t)(p.row_off[t1] - p.row_off[t0]) * 128u;
-            umma_bf16(tmem_base + (uint32_t)(j * 64), make_smem_desc(a0, lbo, 1024), db, kIdesc, first ? 0u : 1u);
-          }
-          first = false;
+        for (int j = 0; j < 5; ++j) {
+          // accumulator j holds taps (2j, 2j+1); the last one pairs (7, 8): tap 7 is computed twice
+          const int t0 = j < 4 ? 2 * j : 7, t1 = t0 + 1;
+          da0[j] = make_smem_desc(x_src + (uint32_t)p.row_off[t0] * 128u,
+                                  (uint32_t)(p.row_off[t1] - p.row_off[t0]) * 128u, 1024);
+        }
+#pragma unroll 2
+        for (int k = 0; k < ksteps; ++k) {                 // 16 positions = +128 in the 16-byte address field
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            umma_bf16(tmem_base + (uint32_t)(j * 64), da0[j] + (uint64_t)(128 * k), db0 + (uint64_t)(128 * k), kIdesc,
+                      (first && k == 0) ? 0u : 1u);
         }
         umma_commit(empty_bar(buf));
-        if (++buf == 2) { buf = 0; phase ^= 1u; }
       }
-      umma_commit(tfull);
+      __syncwarp();
+      first = false;
+      if (++buf == p.nbuf) { buf = 0; phase ^= 1u; }
     }
+    if (elect_one()) umma_commit(tfull);
+    __syncwarp();
   } else {
     const int quad = warp & 3;
     mbar_wait(tfull, 0);
@@ -312,20 +320,33 @@ static bool halo_geom(const ConvGeom& g, int kred, HaloParams* p, size_t smem_fi
   while (wp < g.in_w + 2) wp *= 2;
   if (wp > 128 || g.in_w * 4 < wp * 3) return false;          // < 75 % useful positions: not worth it
   const int rt = 128 / wp;
-  int best_t = 0; long long best_cost = 0;
-  for (int t = 1; t <= 8; ++t) {
-    const int r = rt * t;
-    const size_t a_buf = ((size_t)((r + 2) * wp + 8) * 128 + 1023) / 1024 * 1024;
-    const size_t need = smem_fixed + 2 * (a_buf + (dy_tile ? (size_t)r * wp * 128 : 0)) + 2048;
-    if (need > 227 * 1024) break;
-    const long long strips = (g.in_h + r - 1) / r;
-    const long long cost = strips * (r + 2) * 16 + strips * r * 16 + strips * 8;   // rows fetched + rows computed
-    if (best_t == 0 || cost < best_cost) { best_t = t; best_cost = cost; }
-    if (r >= g.in_h) break;
-  }
+  // Strip height R = rt*T and the number of halo tiles in flight.  One TMA box per strip means the
+  // load pipeline is only as deep as the buffers: prefer >= 3 buffers (measured: the kernels are
+  // load-latency bound with 2), then the tallest strip (smallest halo overhead (R+2)/R).
+  int best_t = 0, best_nbuf = 0; long long best_cost = 0;
+  for (int nbuf = 2; nbuf <= 4; ++nbuf)
+    for (int t = 1; t <= 8; ++t) {
+      const int r = rt * t;
+      const size_t a_buf = ((size_t)((r + 2) * wp + 8) * 128 + 1023) / 1024 * 1024;
+      const size_t need = smem_fixed + nbuf * (a_buf + (dy_tile ? (size_t)r * wp * 128 : 0)) + 2048;
+      if (need > 227 * 1024) break;
+      const long long strips = (g.in_h + r - 1) / r;
+      // rows fetched + rows computed per image, scaled by a pipeline-depth penalty
+      long long cost = (strips * (r + 2) + strips * r) * 16 + strips * 8;
+      if (nbuf == 2) cost = cost * 3 / 2;
+      if (best_t == 0 || cost < best_cost) { best_t = t; best_nbuf = nbuf; best_cost = cost; }
+      if (r >= g.in_h) break;
+    }
   if (best_t == 0) return false;
+  if (g_halo_t > 0 && g_halo_nbuf >= 2 && g_halo_nbuf <= 4) {        // experiment override (RIGL_HALO_CFG=T,NBUF)
+    const int r = rt * g_halo_t;
+    const size_t a_buf = ((size_t)((r + 2) * wp + 8) * 128 + 1023) / 1024 * 1024;
+    if (smem_fixed + g_halo_nbuf * (a_buf + (dy_tile ? (size_t)r * wp * 128 : 0)) + 2048 <= 227 * 1024) {
+      best_t = g_halo_t; best_nbuf = g_halo_nbuf;
+    }
+  }
   p->W = g.in_w; p->H = g.in_h; p->NB = g.batch; p->Wp = wp;
-  p->T = best_t; p->R = rt * best_t;
+  p->T = best_t; p->R = rt * best_t; p->nbuf = best_nbuf;
   p->strips_per_image = (g.in_h + p->R - 1) / p->R;
   p->total_strips = p->strips_per_image * g.batch;
   p->a_tx_bytes = (uint32_t)((p->R + 2) * wp) * 128u;
@@ -374,7 +395,7 @@ static int halo_launch_kmajor(HaloParams p, const void* in, int kred, int in_pit
   const uint32_t obox[4] = {64, (uint32_t)p.Wp, (uint32_t)(128 / p.Wp), 1};
   rc = make_act_map(&omap, out, p.NB, p.H, p.W, n_out, out_pitch, 1, 0, 0, obox);
   if (rc != RIGL_OK) return rc;
-  const size_t smem = 9 * kHaloBTapBytes + 2 * (size_t)p.a_buf_bytes + 2 * kHaloSlabBytes + 1024 + 256;
+  const size_t smem = 9 * kHaloBTapBytes + p.nbuf * (size_t)p.a_buf_bytes + 2 * kHaloSlabBytes + 1024 + 256;
   static size_t configured = 0;
   if (smem > configured) {
     RIGL_CUDA(cudaFuncSetAttribute(k_halo3x3_kmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -404,7 +425,7 @@ static int halo_launch_wgrad(HaloParams p, const ConvGeom& g, const void* x, con
   const uint32_t dbox[4] = {64, (uint32_t)p.Wp, (uint32_t)p.R, 1};
   rc = make_act_map(&dymap, dy, p.NB, p.H, p.W, g.cout, g.cout, 1, 0, 0, dbox);
   if (rc != RIGL_OK) return rc;
-  const size_t smem = 2 * ((size_t)p.a_buf_bytes + (size_t)p.R * p.Wp * 128) + 1024 + 256;
+  const size_t smem = p.nbuf * ((size_t)p.a_buf_bytes + (size_t)p.R * p.Wp * 128) + 1024 + 256;
   static size_t configured = 0;
   if (smem > configured) {
     RIGL_CUDA(cudaFuncSetAttribute(k_halo3x3_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

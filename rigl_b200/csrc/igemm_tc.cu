@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -200,7 +201,10 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and ONE ELECTED lane issues: with an elect.sync
+    // predicate the descriptors stay in uniform registers (a `lane == 0` test costs ~13 extra
+    // instructions per MMA, more than a 128 x 64 x 16 MMA takes to execute).
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
@@ -214,21 +218,22 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
             if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_src = smem_base + stage * kStageBytes;
-            const uint32_t b_src = a_src + kABytes;
+            if (elect_one()) {
+              const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
+              const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_src + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc(b_src + k * 32, 16, 1024);
-              umma_bf16(d_tmem, da, db, kIdesc, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < kBK / 16; ++k)          // +32 bytes along K = +2 in the 16-byte address field
+                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);   // release the slot in BOTH CTAs
+              else umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
             }
+            __syncwarp();
             first = false;
-            if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);   // release the slot in BOTH CTAs
-            else umma_commit(empty_bar(stage));            // frees the smem slot when the MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit(tfull_bar(acc));                       // accumulator complete
+        if (elect_one()) umma_commit(tfull_bar(acc));      // accumulator complete
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -480,8 +485,8 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only; converged warp, one elected lane) =====================
+    if (leader) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
@@ -495,20 +500,21 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
             if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_src = smem_base + stage * kStageBytes;
-            const uint32_t b_src = a_src + kABytes;
+            if (elect_one()) {
+              const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
+              const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_src + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc(b_src + k * 32, 16, 1024);
-              umma_bf16_2cta(d_tmem, da, db, kIdesc, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              umma_commit_2cta_mc(empty_bar(stage), kPairMask);     // slot free in BOTH CTAs
             }
+            __syncwarp();
             first = false;
-            umma_commit_2cta_mc(empty_bar(stage), kPairMask);     // slot free in BOTH CTAs
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit_2cta_mc(tfull_bar(acc), kPairMask);           // accumulator ready in BOTH CTAs
+        if (elect_one()) umma_commit_2cta_mc(tfull_bar(acc), kPairMask);   // accumulator ready in BOTH CTAs
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -703,7 +709,7 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                      // converged warp, one elected lane issues
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int q = cluster_id; q < total_groups; q += n_clusters) {
@@ -716,20 +722,20 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
         for (int pb = pb0; pb < pb1; ++pb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_src = smem_base + stage * kStageBytes;
-          const uint32_t b_src = a_src + kABytes;
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, kBox, 1024);
+            const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, kBox, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // 16 pixels = 16 rows of 128 B further down the box
-            const uint64_t da = make_smem_desc(a_src + k * 16 * 128, kBox, 1024);
-            const uint64_t db = make_smem_desc(b_src + k * 16 * 128, kBox, 1024);
-            umma_bf16(d_tmem, da, db, kIdesc, (pb == pb0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < kBK / 16; ++k)            // 16 pixels = 16 rows of 128 B = +128 address units
+              umma_bf16(d_tmem, da + 128 * k, db + 128 * k, kIdesc, (pb == pb0 && k == 0) ? 0u : 1u);
+            if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);
+            else umma_commit(empty_bar(stage));
           }
-          if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);
-          else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (elect_one()) umma_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -814,6 +820,7 @@ static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
 static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
+static int g_halo_t = 0, g_halo_nbuf = 0;   // RIGL_HALO_CFG=T,NBUF: tuning override for the halo kernels
 static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
                                     // on ResNet-50 b256: the main loops are not L2-bandwidth bound)
 static int g_num_sms = 0;
@@ -834,6 +841,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_HALO_CFG")) sscanf(e, "%d,%d", &g_halo_t, &g_halo_nbuf);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
