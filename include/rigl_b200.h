@@ -231,6 +231,15 @@ RIGL_API int rigl_bn_backward(const void* da, const void* y, const void* act, co
                               const float* save_rstd, const float* save_scale, const float* save_shift,
                               int64_t rows, int channels, int relu, void* dy, void* dresidual,
                               float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+/* Same with the output gradient given as TWO addends, da + da2 (da2 may be NULL): the output of a
+ * residual block feeds both the next block's first conv and its shortcut, and TensorFlow's
+ * gradient aggregation (an AddN per forked tensor) would otherwise be a separate elementwise pass.
+ * The sum is rounded to bf16 exactly like that separate add.  Residual form only. */
+RIGL_API int rigl_bn_backward2(const void* da, const void* da2, const void* y, const void* act,
+                               const float* save_mean, const float* save_rstd, const float* save_scale,
+                               const float* save_shift, int64_t rows, int channels, int relu, void* dy,
+                               void* dresidual, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                               void* stream);
 
 /* Max pooling, NHWC bf16, TF 'SAME' padding (out = ceil(in/stride), pad_before = pad_total/2).
  * Replaces tf.layers.max_pooling2d(pool_size=3, strides=2, padding='SAME'),

@@ -46,6 +46,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <int MODE>
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ da,
+            const __nv_bfloat16* __restrict__ da2 /* MODE 2: optional second addend of the output gradient */,
             const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ gout,
             const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
             const float* __restrict__ shift, int relu, long long rows, int C, long long rows_per_block,
@@ -72,7 +73,7 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
     if (r_in < rpi) {
       // 4 rows per trip: all loads are issued before any arithmetic (memory-level parallelism)
       for (long long rb = row0 + r_in; rb < row1; rb += 4ll * rpi) {
-        uint4 qy[4], qd[4], qa[4];
+        uint4 qy[4], qd[4], qa[4], qe[4];
         bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -82,7 +83,10 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
             const long long off = r * C + 8 * v;
             qy[u] = *reinterpret_cast<const uint4*>(y + off);
             if (MODE != 0) qd[u] = *reinterpret_cast<const uint4*>(da + off);
-            if (MODE == 2) qa[u] = *reinterpret_cast<const uint4*>(act + off);
+            if (MODE == 2) {
+              qa[u] = *reinterpret_cast<const uint4*>(act + off);
+              if (da2) qe[u] = *reinterpret_cast<const uint4*>(da2 + off);
+            }
           }
         }
 #pragma unroll
@@ -98,6 +102,12 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
             float g[8];
             unpack8(qd[u], g);
             if (MODE == 2) {
+              if (da2) {       // the block output feeds two consumers: their gradients are summed here
+                float g2[8];   // (rounded to bf16 like the separate elementwise add it replaces)
+                unpack8(qe[u], g2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = __bfloat162float(__float2bfloat16(g[i] + g2[i]));
+              }
               float fa[8];
               unpack8(qa[u], fa);
 #pragma unroll
@@ -335,8 +345,8 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
   }
   float* partial = static_cast<float*>(ws);
   k_bn_colsum<0><<<nb, kBnThreads, colsum_smem(channels), s>>>(
-      (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels, rpb,
-      partial);
+      (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels,
+      rpb, partial);
   RIGL_LAUNCH_CHECK("k_bn_colsum<0>");
   k_bn_finalize_fwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, nb, channels, rows, eps, gamma, beta,
                                                                   save_mean, save_rstd, save_scale, save_shift,
@@ -397,6 +407,17 @@ extern "C" int rigl_bn_backward(const void* da, const void* y, const void* act, 
                                 const float* save_rstd, const float* save_scale, const float* save_shift,
                                 int64_t rows, int channels, int relu, void* dy, void* dresidual, float* dgamma,
                                 float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
+  return rigl_bn_backward2(da, nullptr, y, act, save_mean, save_rstd, save_scale, save_shift, rows, channels, relu, dy,
+                           dresidual, dgamma, dbeta, ws, ws_bytes, stream_);
+}
+
+extern "C" int rigl_bn_backward2(const void* da, const void* da2, const void* y, const void* act,
+                                 const float* save_mean, const float* save_rstd, const float* save_scale,
+                                 const float* save_shift, int64_t rows, int channels, int relu, void* dy,
+                                 void* dresidual, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                                 void* stream_) {
+  RIGL_REQUIRE(da2 == nullptr || (dresidual != nullptr && aligned16(da2)),
+               "rigl_bn_backward2: a second output gradient needs the residual form (dresidual != NULL)");
   RIGL_REQUIRE(da && y && save_mean && save_rstd && save_scale && save_shift && dy && dgamma && dbeta && ws,
                "rigl_bn_backward: null argument");
   RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, "rigl_bn_backward: channels must be a multiple of 8");
@@ -414,12 +435,12 @@ extern "C" int rigl_bn_backward(const void* da, const void* y, const void* act, 
   const bool residual_form = dresidual != nullptr;
   if (residual_form) {
     k_bn_colsum<2><<<nb, kBnThreads, colsum_smem(channels), s>>>(
-        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, (const __nv_bfloat16*)act, (__nv_bfloat16*)dresidual,
-        save_mean, save_rstd, save_scale, save_shift, relu, rows, channels, rpb, partial);
+        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, (const __nv_bfloat16*)da2, (const __nv_bfloat16*)act,
+        (__nv_bfloat16*)dresidual, save_mean, save_rstd, save_scale, save_shift, relu, rows, channels, rpb, partial);
     RIGL_LAUNCH_CHECK("k_bn_colsum<2>");
   } else {
     k_bn_colsum<1><<<nb, kBnThreads, colsum_smem(channels), s>>>(
-        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, nullptr, nullptr, save_mean, save_rstd, save_scale,
+        (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, nullptr, nullptr, nullptr, save_mean, save_rstd, save_scale,
         save_shift, relu, rows, channels, rpb, partial);
     RIGL_LAUNCH_CHECK("k_bn_colsum<1>");
   }

@@ -20,7 +20,7 @@ def _p(t):
 class _BNFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, y, gamma, beta, residual, mod, partial):
+  def forward(ctx, y, gamma, beta, residual, mod, partial, fork=False):
     n, c, h, w = y.shape
     rows = n * h * w
     dev = y.device
@@ -42,31 +42,48 @@ class _BNFn(torch.autograd.Function):
           save[1].data_ptr(), save[2].data_ptr(), save[3].data_ptr(), out.data_ptr(), ws.data_ptr(),
           ws.numel(), _cabi.stream_ptr()), 'rigl_bn_forward_train')
     _timed('bn_fwd', mod, run)
-    ctx.mod, ctx.has_res = mod, residual is not None
+    ctx.mod, ctx.has_res, ctx.fork = mod, residual is not None, bool(fork)
     ctx.save_for_backward(y, out if residual is not None else None, save)
+    if fork:
+      # Two handles on the same activation for its two consumers (next block's first conv and its
+      # shortcut): backward then receives their gradients SEPARATELY and the sum is folded into
+      # the column-sum pass (rigl_bn_backward2) instead of autograd's elementwise add.
+      ctx.set_materialize_grads(False)
+      return out, out.detach()
     return out
 
   @staticmethod
-  def backward(ctx, da):
+  def backward(ctx, da, da_b=None):
     y, act, save = ctx.saved_tensors
     mod = ctx.mod
     n, c, h, w = y.shape
     rows = n * h * w
-    da = da.contiguous(memory_format=torch.channels_last)
-    if da.dtype != torch.bfloat16:
-      da = da.to(torch.bfloat16)
+
+    def as_grad(t):
+      t = t.contiguous(memory_format=torch.channels_last)
+      return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+    if ctx.fork:
+      if da is None and da_b is None:
+        return None, None, None, None, None, None, None
+      if da is None:
+        da, da_b = da_b, None
+    da = as_grad(da)
+    if da_b is not None:
+      da_b = as_grad(da_b)
+      if not ctx.has_res:           # only the residual form sums in-kernel
+        da, da_b = da + da_b, None
     dy = torch.empty_like(y, memory_format=torch.channels_last)
     dres = torch.empty_like(y, memory_format=torch.channels_last) if ctx.has_res else None
     dgb = torch.empty((2, c), dtype=torch.float32, device=y.device)
     ws = _workspace(y.device, _cabi.lib().rigl_bn_workspace_bytes(rows, c) + 8 * c + 256)
 
     def run():
-      _cabi.check(_cabi.lib().rigl_bn_backward(
-          da.data_ptr(), y.data_ptr(), _p(act), save[0].data_ptr(), save[1].data_ptr(), save[2].data_ptr(),
-          save[3].data_ptr(), rows, c, int(mod.relu), dy.data_ptr(), _p(dres), dgb[0].data_ptr(),
-          dgb[1].data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr()), 'rigl_bn_backward')
+      _cabi.check(_cabi.lib().rigl_bn_backward2(
+          da.data_ptr(), _p(da_b), y.data_ptr(), _p(act), save[0].data_ptr(), save[1].data_ptr(),
+          save[2].data_ptr(), save[3].data_ptr(), rows, c, int(mod.relu), dy.data_ptr(), _p(dres),
+          dgb[0].data_ptr(), dgb[1].data_ptr(), ws.data_ptr(), ws.numel(), _cabi.stream_ptr()), 'rigl_bn_backward2')
     _timed('bn_bwd', mod, run)
-    return dy, dgb[0], dgb[1], dres, None, None
+    return dy, dgb[0], dgb[1], dres, None, None, None
 
 
 class FusedBatchNormReLU(nn.Module):
@@ -84,9 +101,11 @@ class FusedBatchNormReLU(nn.Module):
     self.register_buffer('running_mean', torch.zeros(channels, device=device))
     self.register_buffer('running_var', torch.ones(channels, device=device))
 
-  def forward(self, y, residual=None, producer=None):
+  def forward(self, y, residual=None, producer=None, fork=False):
     """`producer`: the SparseConv2d whose output `y` is; if its epilogue emitted the batch statistics
-    of exactly this tensor (layer.bn_partial), the stats pass is skipped."""
+    of exactly this tensor (layer.bn_partial), the stats pass is skipped.
+    `fork`: return the activation TWICE (same storage) for its two consumers; their gradients are
+    then summed inside the backward kernel instead of by a separate elementwise add."""
     if y.dim() != 4 or y.shape[1] != self.channels:
       raise ValueError('expected [N,%d,H,W]' % self.channels)
     partial = None
@@ -101,7 +120,7 @@ class FusedBatchNormReLU(nn.Module):
     if residual is not None:
       residual = residual.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     if self.training:
-      return _BNFn.apply(y, self.weight, self.bias, residual, self, partial)
+      return _BNFn.apply(y, self.weight, self.bias, residual, self, partial, fork)
     scale = self.weight.detach() * torch.rsqrt(self.running_var + self.eps)
     shift = self.bias.detach() - self.running_mean * scale
     out = torch.empty_like(y, memory_format=torch.channels_last)
@@ -109,7 +128,7 @@ class FusedBatchNormReLU(nn.Module):
     _cabi.check(_cabi.lib().rigl_bn_apply(y.data_ptr(), _p(residual), scale.data_ptr(), shift.data_ptr(),
                                           n * h * w, c, int(self.relu), out.data_ptr(), _cabi.stream_ptr()),
                 'rigl_bn_apply')
-    return out
+    return (out, out) if fork else out
 
 
 class _MaxPoolFn(torch.autograd.Function):

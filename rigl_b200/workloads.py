@@ -31,6 +31,11 @@ def _BNReLU(channels, relu=True, init_zero=False, device='cuda'):
                             decay=BATCH_NORM_DECAY, device=device)
 
 
+# Block outputs are handed to their two consumers as two handles so that the gradient sum happens
+# inside the BN backward kernel (rigl_bn_backward2) rather than in a separate elementwise add.
+FORK_BLOCK_OUTPUTS = True
+
+
 class _Bottleneck(nn.Module):
 
   def __init__(self, cin, filters, strides, use_projection, name, device, registry):
@@ -52,12 +57,16 @@ class _Bottleneck(nn.Module):
     # last BN of the block: zero-init gamma; the residual add + final ReLU are fused into it
     self.bn3 = _BNReLU(4 * filters, relu=True, init_zero=True, device=device)
 
-  def forward(self, x):
+  def forward(self, x, x_skip=None, fork=False):
+    """`x` feeds conv1, `x_skip` (the same activation, second handle) the shortcut branch; with
+    `fork` the block output comes back as two handles as well (see FusedBatchNormReLU.forward)."""
     # every conv feeds a BN: its epilogue emits that BN's batch statistics (producer=...)
-    shortcut = x if self.proj is None else self.proj_bn(self.proj(x), producer=self.proj)
+    if x_skip is None:
+      x_skip = x
+    shortcut = x_skip if self.proj is None else self.proj_bn(self.proj(x_skip), producer=self.proj)
     y = self.bn1(self.conv1(x), producer=self.conv1)
     y = self.bn2(self.conv2(y), producer=self.conv2)
-    return self.bn3(self.conv3(y), residual=shortcut, producer=self.conv3)   # relu(BN(conv3) + shortcut)
+    return self.bn3(self.conv3(y), residual=shortcut, producer=self.conv3, fork=fork)   # relu(BN(conv3) + shortcut)
 
 
 class ResNet50(nn.Module):
@@ -89,8 +98,13 @@ class ResNet50(nn.Module):
   def forward(self, x):
     x = self.initial_bn(self.initial_conv(x), producer=self.initial_conv)
     x = max_pool_same(x, 3, 2)                      # 'SAME' 3x3/2 pool, resnet_model.py:636-642
-    for blk in self.blocks:
-      x = blk(x)
+    x_skip, last = x, len(self.blocks) - 1
+    for i, blk in enumerate(self.blocks):
+      if i < last and FORK_BLOCK_OUTPUTS:
+        x, x_skip = blk(x, x_skip, fork=True)
+      else:
+        x = blk(x, x_skip)
+        x_skip = x
     x = x.mean(dim=(2, 3))
     return self.final_dense(x)
 

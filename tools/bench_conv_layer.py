@@ -22,6 +22,8 @@ SHAPES = {
     # n, h, w, cin, cout, k, stride
     'r50s1': [(256, 56, 56, 64, 64, 3, 1)],
     'r50s2': [(256, 28, 28, 128, 128, 3, 1)],
+    'r50_c3': [(256, 14, 14, 1024, 256, 1, 1)],
+    'r50_33c3': [(256, 14, 14, 256, 256, 3, 1)],
     'r50_3x3': [(256, 56, 56, 64, 64, 3, 1), (256, 28, 28, 128, 128, 3, 1), (256, 14, 14, 256, 256, 3, 1),
                 (256, 7, 7, 512, 512, 3, 1)],
     'r50_1x1': [(256, 56, 56, 64, 256, 1, 1), (256, 56, 56, 256, 64, 1, 1), (256, 28, 28, 512, 128, 1, 1),
