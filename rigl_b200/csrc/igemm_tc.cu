@@ -83,6 +83,28 @@ __device__ __forceinline__ bool weight_block_live(const IgemmParams& p, int tap_
   return s != 0;
 }
 
+
+// Liveness of every (tap, K block) of one N tile as a bitmask in shared memory, computed by a
+// whole warp at the start of a tile (one round of parallel loads) instead of by the issuing
+// thread once per K block: the single-thread TMA / MMA issue loops are instruction-latency bound
+// (about 900 clk per stage with the survivor-table loads inline, which hid the TMA and tensor
+// limits), so everything that can leave them does.  Block 0 is always live (it initialises D).
+constexpr int kLiveWords = 10;        // 320 (tap, K block) pairs; longer reductions run without skipping
+template <int kBN64>
+__device__ __forceinline__ bool build_live_mask(const IgemmParams& p, int n_tile, int lane, uint32_t* mask_smem) {
+  const int nkb = p.ntaps * p.kblks;
+  if (p.nnz == nullptr || nkb > kLiveWords * 32) return false;       // no table (or too long): everything is live
+  for (int w = 0; w * 32 < nkb; ++w) {
+    const int j = w * 32 + lane;
+    bool live = true;
+    if (j > 0 && j < nkb) live = weight_block_live(p, j / p.kblks, n_tile, j % p.kblks, kBN64);
+    const uint32_t m = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) mask_smem[w] = m;
+  }
+  __syncwarp();
+  return true;
+}
+
 // ----------------------------------------------------------------------------
 // fprop / dgrad kernel: D[128 pixels, BN] += A[128, 64] * B[BN, 64]^T per (tap, k block)
 // ----------------------------------------------------------------------------
@@ -141,6 +163,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  __shared__ uint32_t live_prod[kLiveWords], live_mma[kLiveWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
@@ -167,8 +190,8 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
   constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
         const int n_tile = pair % p.n_tiles;
@@ -176,24 +199,27 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        bool first = true;
+        const bool masked = build_live_mask<kBN64>(p, n_tile, lane, live_prod);
+        int j = 0;
         for (int t = 0; t < p.ntaps; ++t) {
           const TapInfo tap = p.taps[t];
-          for (int kb = 0; kb < p.kblks; ++kb) {
-            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
-            first = false;
+          for (int kb = 0; kb < p.kblks; ++kb, ++j) {
+            if (masked && !((live_prod[j >> 5] >> (j & 31)) & 1u)) continue;
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * kStageBytes;
-            const uint32_t b_dst = a_dst + kABytes;
-            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_4d(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
-                        th * p.bh + tap.dh, tn * p.bn);
-            if (CL > 1) {     // my half of the weight tile, multicast to every CTA of the cluster
-              tma_load_3d_mc(b_dst + cta_rank * (uint32_t)(BN / CL) * 128u, &bmap, full_bar(stage), kb * kBK,
-                             n_tile * BN + (int)cta_rank * (BN / CL), tap.b_tap, kMcMask);
-            } else {
-              tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN, tap.b_tap);
+            if (elect_one()) {
+              const uint32_t a_dst = smem_base + stage * kStageBytes;
+              const uint32_t b_dst = a_dst + kABytes;
+              mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_4d(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                          th * p.bh + tap.dh, tn * p.bn);
+              if (CL > 1) {     // my half of the weight tile, multicast to every CTA of the cluster
+                tma_load_3d_mc(b_dst + cta_rank * (uint32_t)(BN / CL) * 128u, &bmap, full_bar(stage), kb * kBK,
+                               n_tile * BN + (int)cta_rank * (BN / CL), tap.b_tap, kMcMask);
+              } else {
+                tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN, tap.b_tap);
+              }
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -212,25 +238,25 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const bool masked = build_live_mask<kBN64>(p, n_tile, lane, live_mma);
         bool first = true;
-        for (int t = 0; t < p.ntaps; ++t) {
-          for (int kb = 0; kb < p.kblks; ++kb) {
-            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
-              const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
+        const int nkb = p.ntaps * p.kblks;
+        for (int j = 0; j < nkb; ++j) {
+          if (masked && !((live_mma[j >> 5] >> (j & 31)) & 1u)) continue;
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
+            const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k)          // +32 bytes along K = +2 in the 16-byte address field
-                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
-              if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);   // release the slot in BOTH CTAs
-              else umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
-            }
-            __syncwarp();
-            first = false;
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            for (int k = 0; k < kBK / 16; ++k)          // +32 bytes along K = +2 in the 16-byte address field
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+            if (CL > 1) umma_commit_mc(empty_bar(stage), kMcMask);   // release the slot in BOTH CTAs
+            else umma_commit(empty_bar(stage));          // frees the smem slot when the MMAs retire
           }
+          __syncwarp();
+          first = false;
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) umma_commit(tfull_bar(acc));      // accumulator complete
         __syncwarp();
@@ -431,6 +457,7 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  __shared__ uint32_t live_prod[kLiveWords], live_mma[kLiveWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
@@ -455,8 +482,8 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
   constexpr int kBN64 = (BN + 63) / 64;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
         const int n_tile = pair % p.n_tiles;
@@ -464,21 +491,24 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        bool first = true;
+        const bool masked = build_live_mask<kBN64>(p, n_tile, lane, live_prod);
+        int j = 0;
         for (int t = 0; t < p.ntaps; ++t) {
           const TapInfo tap = p.taps[t];
-          for (int kb = 0; kb < p.kblks; ++kb) {
-            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
-            first = false;
+          for (int kb = 0; kb < p.kblks; ++kb, ++j) {
+            if (masked && !((live_prod[j >> 5] >> (j & 31)) & 1u)) continue;
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * kStageBytes;
-            const uint32_t b_dst = a_dst + kABytes;
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes land here
-            else mbar_arrive_leader(full_bar(stage));
-            tma_load_4d_2cta(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
-                             th * p.bh + tap.dh, tn * p.bn);
-            tma_load_3d_2cta(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2),
-                             tap.b_tap);
+            if (elect_one()) {
+              const uint32_t a_dst = smem_base + stage * kStageBytes;
+              const uint32_t b_dst = a_dst + kABytes;
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes land here
+              else mbar_arrive_leader(full_bar(stage));
+              tma_load_4d_2cta(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                               th * p.bh + tap.dh, tn * p.bn);
+              tma_load_3d_2cta(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2),
+                               tap.b_tap);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -494,24 +524,24 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // both epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const bool masked = build_live_mask<kBN64>(p, n_tile, lane, live_mma);
         bool first = true;
-        for (int t = 0; t < p.ntaps; ++t) {
-          for (int kb = 0; kb < p.kblks; ++kb) {
-            if (!first && !weight_block_live(p, t, n_tile, kb, kBN64)) continue;
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
-              const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
+        const int nkb = p.ntaps * p.kblks;
+        for (int j = 0; j < nkb; ++j) {
+          if (masked && !((live_mma[j >> 5] >> (j & 31)) & 1u)) continue;
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
+            const uint64_t db = make_smem_desc(smem_base + stage * kStageBytes + kABytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k)
-                umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
-              umma_commit_2cta_mc(empty_bar(stage), kPairMask);     // slot free in BOTH CTAs
-            }
-            __syncwarp();
-            first = false;
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+            umma_commit_2cta_mc(empty_bar(stage), kPairMask);     // slot free in BOTH CTAs
           }
+          __syncwarp();
+          first = false;
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) umma_commit_2cta_mc(tfull_bar(acc), kPairMask);   // accumulator ready in BOTH CTAs
         __syncwarp();
@@ -667,7 +697,7 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                                      // converged warp, one elected lane issues
       int stage = 0; uint32_t phase = 0;
       for (int q = cluster_id; q < total_groups; q += n_clusters) {
         const int split = q / groups_per_split;
@@ -679,31 +709,33 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
         const int c_base = live ? (mi % p.m_tiles) * kBM : (1 << 28);     // idle partner: out of bounds
         const int pb0 = split * p.pblocks_per_split;
         const int pb1 = min(pb0 + p.pblocks_per_split, p.pblocks);
+        int tw = pb0 % p.tiles_w, th = (pb0 / p.tiles_w) % p.tiles_h, tn = pb0 / (p.tiles_w * p.tiles_h);
         for (int pb = pb0; pb < pb1; ++pb) {
-          const int tw = pb % p.tiles_w;
-          const int th = (pb / p.tiles_w) % p.tiles_h;
-          const int tn = pb / (p.tiles_w * p.tiles_h);
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * kStageBytes;
-          const uint32_t b_dst = a_dst + kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + stage * kStageBytes;
+            const uint32_t b_dst = a_dst + kABytes;
+            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
 #pragma unroll
-          for (int h = 0; h < kBM / 64; ++h)
-            tma_load_4d(a_dst + h * kBox, &xmaps.a[tap.map_id], full_bar(stage), c_base + h * 64,
-                        tw * p.bw + tap.dw, th * p.bh + tap.dh, tn * p.bn);
-          if (CL > 1) {
+            for (int h = 0; h < kBM / 64; ++h)
+              tma_load_4d(a_dst + h * kBox, &xmaps.a[tap.map_id], full_bar(stage), c_base + h * 64,
+                          tw * p.bw + tap.dw, th * p.bh + tap.dh, tn * p.bn);
+            if (CL > 1) {
 #pragma unroll
-            for (int hh = 0; hh < kBBoxes / CL; ++hh) {
-              const int h = (int)cta_rank * (kBBoxes / CL) + hh;
-              tma_load_4d_mc(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
-                             th * p.bh, tn * p.bn, kMcMask);
+              for (int hh = 0; hh < kBBoxes / CL; ++hh) {
+                const int h = (int)cta_rank * (kBBoxes / CL) + hh;
+                tma_load_4d_mc(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
+                               th * p.bh, tn * p.bn, kMcMask);
+              }
+            } else {
+#pragma unroll
+              for (int h = 0; h < kBBoxes; ++h)
+                tma_load_4d(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
+                            th * p.bh, tn * p.bn);
             }
-          } else {
-#pragma unroll
-            for (int h = 0; h < kBBoxes; ++h)
-              tma_load_4d(b_dst + h * kBox, &dymap, full_bar(stage), n_tile * BN + h * 64, tw * p.bw,
-                          th * p.bh, tn * p.bn);
           }
+          __syncwarp();
+          if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }   // next pixel block (no divisions)
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -1039,9 +1071,9 @@ static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bm
                            IgemmParams& p, int bn_tile, cudaStream_t s) {
   p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
   if (kmajor_use_pair(p)) {               // CTA-pair MMA (M = 256); bmap was built with bn_tile/2 rows
-    if (bn_tile == 64) return launch_kmajor2<64, 8>(amaps, bmap, omap, p, s);
-    if (bn_tile == 128) return launch_kmajor2<128, 6>(amaps, bmap, omap, p, s);
-    return launch_kmajor2<256, 5>(amaps, bmap, omap, p, s);
+    if (bn_tile == 64) return launch_kmajor2<64, 9>(amaps, bmap, omap, p, s);
+    if (bn_tile == 128) return launch_kmajor2<128, 8>(amaps, bmap, omap, p, s);
+    return launch_kmajor2<256, 6>(amaps, bmap, omap, p, s);
   }
   const bool mc = kmajor_use_mc(p);                        // multicast needs a partner M tile
   if (bn_tile == 64) return mc ? launch_kmajor<64, 8, 2>(amaps, bmap, omap, p, s) : launch_kmajor<64, 8, 1>(amaps, bmap, omap, p, s);

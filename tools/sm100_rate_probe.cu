@@ -17,9 +17,44 @@
 
 using namespace rigl::ptx;
 
+static CUtensorMap g_map;
+static long long* g_fill = nullptr;
+static int g_fill_boxes = 0;
+
+static void report_fill(int grid, int boxes) {
+  if (!boxes) return;
+  std::vector<long long> f(grid);
+  cudaMemcpy(f.data(), g_fill, grid * 8, cudaMemcpyDeviceToHost);
+  std::sort(f.begin(), f.end());
+  printf("        concurrent fills: %d boxes in median %lld clk -> %.2f B/clk/SM\n", boxes, f[grid / 2],
+         (double)boxes * 16384.0 / (double)f[grid / 2]);
+}
+
+
+// Background TMA traffic: one elected lane streams `boxes` 16 KB boxes into a private 4-slot ring
+// (it waits for a slot's previous load itself), so the MMA operand fetch shares the shared-memory
+// port and the TMA unit with fills exactly as in a GEMM main loop.  Returns its own duration.
+__device__ __forceinline__ long long fill_stream(const CUtensorMap* map, uint32_t ring, uint64_t* bars, int boxes) {
+  const long long t0 = clock64();
+  if (elect_one()) {
+    const int row0 = (int)blockIdx.x * 4096;
+    for (int i = 0; i < boxes; ++i) {
+      const int s = i & 3;
+      if (i >= 4) mbar_wait(smem_u32(&bars[s]), ((i >> 2) - 1) & 1);
+      mbar_arrive_expect_tx(smem_u32(&bars[s]), 16384);
+      tma_load_3d(ring + s * 16384, map, smem_u32(&bars[s]), 0, row0 + (i & 31) * 128, 0);
+    }
+    for (int i = boxes; i < boxes + 4; ++i) mbar_wait(smem_u32(&bars[i & 3]), ((i >> 2) - 1) & 1);
+  }
+  __syncwarp();
+  return clock64() - t0;
+}
+
 // ---------------------------------------------------------------- MMA rate
 template <int N, int MN_MAJOR>
-__global__ void __launch_bounds__(128, 1) k_mma_rate(int iters, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) k_mma_rate(int iters, long long* cycles, const __grid_constant__ CUtensorMap fmap,
+                                                     int fill_boxes, long long* fill_cycles) {
+  __shared__ uint64_t fbar[4];
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar;
@@ -30,12 +65,17 @@ __global__ void __launch_bounds__(128, 1) k_mma_rate(int iters, long long* cycle
   for (uint32_t i = tid * 16u; i < 2 * kStage; i += 128 * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i), "r"(0u) : "memory");
   fence_proxy_async_smem();
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&fbar[i]), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (warp == 2 && fill_boxes > 0) {
+    const long long d = fill_stream(&fmap, base + 2 * kStage, fbar, fill_boxes);
+    if (elect_one()) fill_cycles[blockIdx.x] = d;
+    __syncwarp();
+  }
   if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(128, N, MN_MAJOR, MN_MAJOR);
     long long t0 = 0, t1 = 0;
@@ -76,7 +116,10 @@ __device__ __forceinline__ void umma_bf16_2cta_plain(uint32_t tmem_d, uint64_t d
 }
 
 template <int N, int MASKED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_mma2_rate(int iters, long long* cycles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_mma2_rate(int iters, long long* cycles,
+                                                                                 const __grid_constant__ CUtensorMap fmap,
+                                                                                 int fill_boxes, long long* fill_cycles) {
+  __shared__ uint64_t fbar[4];
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar;
@@ -87,12 +130,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_mma2_rate(
   for (uint32_t i = tid * 16u; i < 2 * kStage; i += 128 * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i), "r"(0u) : "memory");
   fence_proxy_async_smem();
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&fbar[i]), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc_2cta(smem_u32(&tmem_slot), 512);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (warp == 2 && fill_boxes > 0) {
+    const long long d = fill_stream(&fmap, base + 2 * kStage, fbar, fill_boxes);
+    if (elect_one()) fill_cycles[blockIdx.x] = d;
+    __syncwarp();
+  }
   if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
     long long t0 = clock64();
@@ -124,12 +172,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_mma2_rate(
 template <int N, int MASKED>
 static void run_mma2(int sms, long long* d_cycles, const char* name) {
   const int iters = 2000;
-  const int smem = 2 * (128 * 64 * 2 + (N / 2) * 64 * 2) + 2048;
+  const int boxes = g_fill_boxes ? (int)(iters * 4.0 * (N / 2) * 1.6 / 300.0) : 0;
+  const int smem = 2 * (128 * 64 * 2 + (N / 2) * 64 * 2) + 4 * 16384 + 2048;
   cudaFuncSetAttribute(k_mma2_rate<N, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = sms / 2 * 2;
   std::vector<long long> h(grid);
   for (int rep = 0; rep < 2; ++rep) {
-    k_mma2_rate<N, MASKED><<<grid, 128, smem>>>(iters, d_cycles);
+    k_mma2_rate<N, MASKED><<<grid, 128, smem>>>(iters, d_cycles, g_map, boxes, g_fill);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); exit(1); }
   }
@@ -137,6 +186,7 @@ static void run_mma2(int sms, long long* d_cycles, const char* name) {
   std::sort(h.begin(), h.end());
   printf("RATE mma2 %-39s clk/MMA median %7.2f  max %7.2f   (floor %d per 256xN)\n", name,
          (double)h[grid / 2] / (iters * 4.0), (double)h.back() / (iters * 4.0), N / 2);
+  report_fill(grid, boxes);
 }
 
 // ---------------------------------------------------------------- TMA rate
@@ -198,11 +248,12 @@ static void report(const char* what, std::vector<long long>& h, double units_per
 template <int N, int MN>
 static void run_mma(int sms, long long* d_cycles, const char* name) {
   const int iters = 2000;
-  const int smem = 2 * (128 * 64 * 2 + N * 64 * 2) + 2048;
+  const int boxes = g_fill_boxes ? (int)(iters * 4.0 * (N / 2 > 48 ? N / 2 : 48) * 1.6 / 300.0) : 0;   // ~ the MMA duration at 54 B/clk
+  const int smem = 2 * (128 * 64 * 2 + N * 64 * 2) + 4 * 16384 + 2048;
   cudaFuncSetAttribute(k_mma_rate<N, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   std::vector<long long> h(sms);
   for (int rep = 0; rep < 2; ++rep) {
-    k_mma_rate<N, MN><<<sms, 128, smem>>>(iters, d_cycles);
+    k_mma_rate<N, MN><<<sms, 128, smem>>>(iters, d_cycles, g_map, boxes, g_fill);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); exit(1); }
   }
@@ -211,6 +262,7 @@ static void run_mma(int sms, long long* d_cycles, const char* name) {
   std::sort(h.begin(), h.end());
   printf("RATE mma %-40s clk/MMA median %7.2f  max %7.2f   (floor %d)\n", name, (double)h[sms / 2] / (iters * 4.0),
          (double)h.back() / (iters * 4.0), N / 2);
+  report_fill(sms, boxes);
 }
 
 int main() {
@@ -219,18 +271,8 @@ int main() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long* d_cycles;
   cudaMalloc(&d_cycles, 1024 * 8);
-  run_mma<64, 0>(sms, d_cycles, "M128 N64  K-major");
-  run_mma<128, 0>(sms, d_cycles, "M128 N128 K-major");
-  run_mma<256, 0>(sms, d_cycles, "M128 N256 K-major");
-  run_mma<64, 1>(sms, d_cycles, "M128 N64  MN-major");
-  run_mma<128, 1>(sms, d_cycles, "M128 N128 MN-major");
-  run_mma<256, 1>(sms, d_cycles, "M128 N256 MN-major");
-  run_mma2<256, 1>(sms, d_cycles, "pair M256 N256 (lane-mask form)");
-  run_mma2<256, 0>(sms, d_cycles, "pair M256 N256 (plain form)");
-  run_mma2<128, 1>(sms, d_cycles, "pair M256 N128 (lane-mask form)");
-  run_mma2<128, 0>(sms, d_cycles, "pair M256 N128 (plain form)");
-  run_mma2<64, 0>(sms, d_cycles, "pair M256 N64 (plain form)");
-
+  long long* d_fill;
+  cudaMalloc(&d_fill, 1024 * 8);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -247,6 +289,27 @@ int main() {
   CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+  g_map = map; g_fill = d_fill;
+  run_mma<64, 0>(sms, d_cycles, "M128 N64  K-major");
+  run_mma<128, 0>(sms, d_cycles, "M128 N128 K-major");
+  run_mma<256, 0>(sms, d_cycles, "M128 N256 K-major");
+  run_mma<64, 1>(sms, d_cycles, "M128 N64  MN-major");
+  run_mma<128, 1>(sms, d_cycles, "M128 N128 MN-major");
+  run_mma<256, 1>(sms, d_cycles, "M128 N256 MN-major");
+  run_mma2<256, 1>(sms, d_cycles, "pair M256 N256 (lane-mask form)");
+  run_mma2<256, 0>(sms, d_cycles, "pair M256 N256 (plain form)");
+  run_mma2<128, 1>(sms, d_cycles, "pair M256 N128 (lane-mask form)");
+  run_mma2<128, 0>(sms, d_cycles, "pair M256 N128 (plain form)");
+  run_mma2<64, 0>(sms, d_cycles, "pair M256 N64 (plain form)");
+  // the same streams with concurrent TMA fills (4 x 16 KB ring per SM)
+  g_fill_boxes = 1;   // sized inside the runners
+  run_mma<256, 0>(sms, d_cycles, "M128 N256 K-major + fills");
+  run_mma<128, 0>(sms, d_cycles, "M128 N128 K-major + fills");
+  run_mma<64, 0>(sms, d_cycles, "M128 N64  K-major + fills");
+  run_mma2<256, 0>(sms, d_cycles, "pair M256 N256 + fills");
+  run_mma2<128, 0>(sms, d_cycles, "pair M256 N128 + fills");
+  g_fill_boxes = 0;
+
   const int smem = kMaxStages * kBoxBytes + 2048;
   cudaFuncSetAttribute(k_tma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   struct Cfg { const char* name; int boxes, stride, window; } cfgs[] = {
