@@ -18,13 +18,13 @@ struct PoolGeom {
 __global__ void __launch_bounds__(256)
 k_maxpool_fwd(PoolGeom g, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
               uint8_t* __restrict__ idx) {
+  // grid = (column tiles, output rows, images), block = (8 channel vectors, 32 columns): no index
+  // divisions in the kernel (they cost more than the window loads).
   const int V = g.c >> 3;
-  const long long total = (long long)g.n * g.oh * g.ow * V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % V);
-    const long long p = i / V;
-    const int ow = (int)(p % g.ow), oh = (int)((p / g.ow) % g.oh), n = (int)(p / ((long long)g.ow * g.oh));
+  const int ow = blockIdx.x * blockDim.y + threadIdx.y, oh = blockIdx.y, n = blockIdx.z;
+  if (ow >= g.ow) return;
+  const long long p = ((long long)n * g.oh + oh) * g.ow + ow;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float best[8];
     uint8_t arg[8];
 #pragma unroll
@@ -61,18 +61,16 @@ __global__ void __launch_bounds__(256)
 k_maxpool_bwd(PoolGeom g, const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
               __nv_bfloat16* __restrict__ dx) {
   const int V = g.c >> 3;
-  const long long total = (long long)g.n * g.h * g.w * V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % V);
-    const long long q = i / V;
-    const int wi = (int)(q % g.w), hi = (int)((q / g.w) % g.h), n = (int)(q / ((long long)g.w * g.h));
+  const int wi = blockIdx.x * blockDim.y + threadIdx.y, hi = blockIdx.y, n = blockIdx.z;
+  if (wi >= g.w) return;
+  const long long q = ((long long)n * g.h + hi) * g.w + wi;
+  // outputs oh with oh*s - pad <= hi <= oh*s - pad + k - 1
+  const int oh_lo = max(0, (hi + g.pad - g.k + g.s) / g.s), oh_hi = min(g.oh - 1, (hi + g.pad) / g.s);
+  const int ow_lo = max(0, (wi + g.pad - g.k + g.s) / g.s), ow_hi = min(g.ow - 1, (wi + g.pad) / g.s);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    // outputs oh with oh*s - pad <= hi <= oh*s - pad + k - 1
-    const int oh_lo = max(0, (hi + g.pad - g.k + g.s) / g.s), oh_hi = min(g.oh - 1, (hi + g.pad) / g.s);
-    const int ow_lo = max(0, (wi + g.pad - g.k + g.s) / g.s), ow_hi = min(g.ow - 1, (wi + g.pad) / g.s);
     for (int oh = oh_lo; oh <= oh_hi; ++oh)
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         const int rel = (hi - (oh * g.s - g.pad)) * g.k + (wi - (ow * g.s - g.pad));
@@ -114,10 +112,9 @@ extern "C" int rigl_maxpool_same_forward(const void* x, int n, int h, int w, int
   int rc = pool_geom(n, h, w, c, ksize, stride, &g);
   if (rc != RIGL_OK) return rc;
   RIGL_REQUIRE(x && y && argmax, "rigl_maxpool_same_forward: null tensor");
-  const long long total = (long long)g.n * g.oh * g.ow * (c / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  k_maxpool_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax);
+  RIGL_REQUIRE(g.oh <= 65535 && n <= 65535, "rigl_maxpool_same_forward: extent too large");
+  const dim3 block(8, 32), grid((unsigned)((g.ow + 31) / 32), (unsigned)g.oh, (unsigned)n);
+  k_maxpool_fwd<<<grid, block, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax);
   RIGL_LAUNCH_CHECK("k_maxpool_fwd");
   return RIGL_OK;
 }
@@ -128,10 +125,9 @@ extern "C" int rigl_maxpool_same_backward(const void* dy, const uint8_t* argmax,
   int rc = pool_geom(n, h, w, c, ksize, stride, &g);
   if (rc != RIGL_OK) return rc;
   RIGL_REQUIRE(dy && dx && argmax, "rigl_maxpool_same_backward: null tensor");
-  const long long total = (long long)g.n * g.h * g.w * (c / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  k_maxpool_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx);
+  RIGL_REQUIRE(g.h <= 65535 && n <= 65535, "rigl_maxpool_same_backward: extent too large");
+  const dim3 block(8, 32), grid((unsigned)((g.w + 31) / 32), (unsigned)g.h, (unsigned)n);
+  k_maxpool_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx);
   RIGL_LAUNCH_CHECK("k_maxpool_bwd");
   return RIGL_OK;
 }
