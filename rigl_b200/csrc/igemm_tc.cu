@@ -66,6 +66,7 @@ struct IgemmParams {
   int nnz_tap_stride, nnz_n_stride, nnz_k_stride;
   int tma_store;                    // 1: epilogue stages bf16 tiles in smem and TMA-stores them
   float* bn_partial;                // optional [gridDim.x][2][N]: per-CTA column sums / sums of squares of D
+  int pair_local;                   // CTA-pair kernel: each CTA's TMA completes on its OWN barrier (see k_igemm_kmajor2)
 };
 
 struct TMaps4 {
@@ -454,6 +455,7 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto peer_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };   // leader: the peer's tile has landed
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -465,7 +467,9 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
     for (int i = 0; i < 4; ++i) prefetch_tmap(&amaps.a[i]);
     prefetch_tmap(&bmap);
     if (p.tma_store) prefetch_tmap(&omap);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), p.pair_local ? 1 : 2); mbar_init(empty_bar(s), 1); mbar_init(peer_bar(s), 1);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     fence_barrier_init();
   }
@@ -501,12 +505,22 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
             if (elect_one()) {
               const uint32_t a_dst = smem_base + stage * kStageBytes;
               const uint32_t b_dst = a_dst + kABytes;
-              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes land here
-              else mbar_arrive_leader(full_bar(stage));
-              tma_load_4d_2cta(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
-                               th * p.bh + tap.dh, tn * p.bn);
-              tma_load_3d_2cta(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2),
-                               tap.b_tap);
+              if (p.pair_local) {
+                // Each CTA's bytes complete on its OWN barrier; the peer's idle MMA warp forwards ONE
+                // cluster-scope arrive per stage to the leader.  (With the loads of both CTAs signalling the
+                // leader's barrier the peer's TMA stream only reached ~33 of the 54 B/clk a lone SM ingests.)
+                mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+                tma_load_4d(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                            th * p.bh + tap.dh, tn * p.bn);
+                tma_load_3d(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2), tap.b_tap);
+              } else {
+                if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * kStageBytes);   // both CTAs' bytes land here
+                else mbar_arrive_leader(full_bar(stage));
+                tma_load_4d_2cta(a_dst, &amaps.a[tap.map_id], full_bar(stage), kb * kBK, tw * p.bw + tap.dw,
+                                 th * p.bh + tap.dh, tn * p.bn);
+                tma_load_3d_2cta(b_dst, &bmap, full_bar(stage), kb * kBK, n_tile * BN + (int)cta_rank * (BN / 2),
+                                 tap.b_tap);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -530,6 +544,7 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
         for (int j = 0; j < nkb; ++j) {
           if (masked && !((live_mma[j >> 5] >> (j & 31)) & 1u)) continue;
           mbar_wait(full_bar(stage), phase);
+          if (p.pair_local) mbar_wait_cluster(peer_bar(stage), phase);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = make_smem_desc(smem_base + stage * kStageBytes, 16, 1024);
@@ -546,6 +561,22 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
         if (elect_one()) umma_commit_2cta_mc(tfull_bar(acc), kPairMask);   // accumulator ready in BOTH CTAs
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    else if (p.pair_local) {
+      // ===== peer CTA: forward "my tile of this stage has landed" to the leader, one arrive per stage =====
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
+        const int n_tile = pair % p.n_tiles;
+        const bool masked = build_live_mask<kBN64>(p, n_tile, lane, live_mma);
+        const int nkb = p.ntaps * p.kblks;
+        for (int j = 0; j < nkb; ++j) {
+          if (masked && !((live_mma[j >> 5] >> (j & 31)) & 1u)) continue;
+          mbar_wait(full_bar(stage), phase);
+          if (elect_one()) mbar_arrive_leader_release(peer_bar(stage));
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else {
@@ -851,6 +882,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
+static bool g_pair_local = false;   // RIGL_PAIR_LOCALBAR=1: per-CTA full barriers + a forwarded arrive (measured 2.5x SLOWER than signalling the leader directly; kept as a documented negative result)
 static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
 static int g_halo_t = 0, g_halo_nbuf = 0;   // RIGL_HALO_CFG=T,NBUF: tuning override for the halo kernels
 static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
@@ -873,6 +905,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_PAIR_LOCALBAR")) g_pair_local = (e[0] == '1');
   if (const char* e = getenv("RIGL_HALO_CFG")) sscanf(e, "%d,%d", &g_halo_t, &g_halo_nbuf);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1042,7 +1075,7 @@ static int launch_kmajor(const TMaps4& amaps, const CUtensorMap& bmap, const CUt
 template <int BN, int STAGES>
 static int launch_kmajor2(const TMaps4& amaps, const CUtensorMap& bmap, const CUtensorMap& omap, const IgemmParams& p,
                           cudaStream_t s) {
-  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + (BN / 2) * kBK * 2) + 2 * (kBM * 64 * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + (BN / 2) * kBK * 2) + 2 * (kBM * 64 * 2) + 1024 + 512;
   static bool configured = false;
   if (!configured) {
     RIGL_CUDA(cudaFuncSetAttribute(k_igemm_kmajor2<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1071,6 +1104,7 @@ static int dispatch_kmajor(int n_out, const TMaps4& amaps, const CUtensorMap& bm
                            IgemmParams& p, int bn_tile, cudaStream_t s) {
   p.n_tiles = (n_out + bn_tile - 1) / bn_tile;
   if (kmajor_use_pair(p)) {               // CTA-pair MMA (M = 256); bmap was built with bn_tile/2 rows
+    p.pair_local = g_pair_local ? 1 : 0;
     if (bn_tile == 64) return launch_kmajor2<64, 9>(amaps, bmap, omap, p, s);
     if (bn_tile == 128) return launch_kmajor2<128, 8>(amaps, bmap, omap, p, s);
     return launch_kmajor2<256, 6>(amaps, bmap, omap, p, s);

@@ -72,6 +72,59 @@ def test_bn_forward_backward(shape, relu, residual):
   assert np.allclose(bn.running_var.cpu().numpy(), 0.9 + 0.1 * var * m / (m - 1), rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize('shape', [(4, 8, 8, 64), (2, 7, 7, 2048), (3, 5, 9, 24)])
+def test_bn_three_kernel_path(shape):
+  """Small tensors take the single-launch (grid-barrier) kernels by default; RIGL_BN_FUSED=0 keeps the
+  3-kernel path (the only one large tensors use) covered at oracle-checkable sizes."""
+  import os, subprocess, sys
+  code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_bn_gpu as t; '
+          '[t.test_bn_forward_backward(%r, relu, res) for relu, res in ((True, False), (False, False), (True, True))]; '
+          'print("BN3_OK")' % (os.path.dirname(os.path.dirname(__file__)), os.path.dirname(__file__), shape))
+  env = dict(os.environ, RIGL_BN_FUSED='0')
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert 'BN3_OK' in out.stdout, out.stdout[-1500:]
+
+
+@pytest.mark.parametrize('shape', [(4, 8, 8, 64), (2, 14, 14, 256), (3, 5, 9, 24)])
+def test_bn_forked_output_sums_two_gradients_in_kernel(shape):
+  """fork=True hands the block output out twice; the two incoming gradients are summed inside the
+  backward column-sum pass (rigl_bn_backward2), rounded to bf16 exactly like the elementwise add
+  (tf AddN / autograd accumulation) it replaces: results are bit-identical to the un-forked BN fed
+  with the pre-added gradient."""
+  n, h, w, c = shape
+  rng = np.random.RandomState(7 + c)
+  y_np = rng.standard_normal(shape) * 1.3
+  r_np = rng.standard_normal(shape)
+  g1_np, g2_np = rng.standard_normal(shape), rng.standard_normal(shape) * 0.5
+  res = {}
+  for fork in (True, False):
+    torch.manual_seed(0)
+    bn = FusedBatchNormReLU(c, relu=True, device=DEV)
+    with torch.no_grad():
+      bn.weight.copy_(torch.linspace(0.5, 1.5, c))
+      bn.bias.copy_(torch.linspace(-0.2, 0.2, c))
+    y = _nhwc_to_dev(y_np).requires_grad_(True)
+    r = _nhwc_to_dev(r_np).requires_grad_(True)
+    g1, g2 = _nhwc_to_dev(g1_np), _nhwc_to_dev(g2_np)
+    if fork:
+      a1, a2 = bn(y, residual=r, fork=True)
+      assert a1.data_ptr() == a2.data_ptr()
+      torch.autograd.backward([a1, a2], [g1, g2])
+    else:
+      a1 = bn(y, residual=r)
+      a1.backward(g1 + g2)                       # bf16 add: the separate elementwise pass
+    res[fork] = (a1.detach().clone(), y.grad.clone(), r.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone())
+  for got, want, what in zip(res[True], res[False], ('out', 'dy', 'dresidual', 'dgamma', 'dbeta')):
+    assert torch.equal(got, want), what
+  # only one consumer used: the other gradient is absent, not zero-filled
+  bn = FusedBatchNormReLU(c, relu=True, device=DEV)
+  y = _nhwc_to_dev(y_np).requires_grad_(True)
+  r = _nhwc_to_dev(r_np).requires_grad_(True)
+  a1, a2 = bn(y, residual=r, fork=True)
+  a2.backward(_nhwc_to_dev(g2_np))
+  assert y.grad is not None and torch.isfinite(y.grad.float()).all()
+
+
 def test_bn_eval_mode_and_errors():
   bn = FusedBatchNormReLU(16, relu=True, device=DEV)
   with torch.no_grad():
