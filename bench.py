@@ -268,7 +268,7 @@ def run_ours(args):
   }
   if world == 1 and not args.no_cpu_baseline:
     out['cpu_baseline'] = cpu_baseline_leg(sample_batch=args.cpu_batch)
-  print(json.dumps(out))
+  _emit(out)
   if dist is not None:
     dist.destroy_process_group()
 
@@ -319,7 +319,7 @@ def run_reference(args):
   t = _cpu_port_timing(batch, steps, warm)
   sec, mu, threads = t['sec_per_step'], t['mask_update_sec'], t['threads']
   value = batch / sec
-  print(json.dumps({
+  _emit({
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/sec',
       'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -329,10 +329,29 @@ def run_reference(args):
                        'sample': 'batch %d, %d step(s), wall %.1fs' % (batch, steps, time.perf_counter() - t0)},
       'mask_update_ms': mu * 1e3,
       'e2e': {'value': value, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-      'gpu_launches': 0}))
+      'gpu_launches': 0})
+
+
+_JSON_FD = None
+
+
+def _emit(obj):
+  """The ONE JSON line of the contract, on the process's original stdout."""
+  line = (json.dumps(obj) + '\n').encode()
+  if _JSON_FD is None:
+    sys.stdout.write(line.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_JSON_FD, line)
 
 
 def main():
+  # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its
+  # version banner there when NCCL_DEBUG is set, library warnings) is sent to stderr.
+  global _JSON_FD
+  sys.stdout.flush()
+  _JSON_FD = os.dup(1)
+  os.dup2(2, 1)
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=100)
