@@ -71,11 +71,41 @@ def _timed(kind, layer, fn):
 
 
 def _workspace(device, nbytes):
-  ws = _WS.get(device)
+  key = (device, _WS_SLOT[0])          # one scratch buffer per (device, stream role)
+  ws = _WS.get(key)
   if ws is None or ws.numel() < nbytes:
     ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-    _WS[device] = ws
+    _WS[key] = ws
   return ws
+
+
+# ---- dense wgrad on a second stream ---------------------------------------------------------------
+# The dense weight gradient of a layer (and mask * grad) is needed only by the optimizer / the mask
+# update, not by the rest of the backward pass, while the chain dgrad -> BN backward -> dgrad ... is
+# serial and half of it (BN) leaves the tensor cores idle.  With WGRAD_SIDE_STREAM the wgrad kernels
+# of layer k run on a forked stream concurrently with the BN backward of layer k-1 (they fit on
+# the same SM: 198 KB + <= 16 KB shared memory).  Opt-in (TrainHarness enables it in CUDA-graph mode):
+# the weight gradient is then written straight into `weight.grad` on the side stream instead of
+# being returned to autograd, and the caller must `join_side_streams()` after `backward()`.
+WGRAD_SIDE_STREAM = False
+_WS_SLOT = ['main']
+_SIDE = {}
+_SIDE_KEEP = []        # tensors the side stream may still be reading (released at the join)
+
+
+def side_stream(device):
+  st = _SIDE.get(device)
+  if st is None:
+    st = torch.cuda.Stream(device=device)
+    _SIDE[device] = st
+  return st
+
+
+def join_side_streams():
+  """The current stream of every device waits for the forked wgrad work; releases the kept tensors."""
+  for dev, st in _SIDE.items():
+    torch.cuda.current_stream(dev).wait_stream(st)
+  del _SIDE_KEEP[:]
 
 
 class NamedParameter(nn.Parameter):
@@ -122,11 +152,28 @@ class _MaskedConvFn(torch.autograd.Function):
     dy16 = layer._as_activation(dy, layer.out_channels)
     dx = _timed('dgrad', layer, lambda: layer._dgrad(dy16, x)) if ctx.needs_input_grad[0] else None
     mw = layer.masked_weights
-    _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
-    mw.fresh = True
     gw = None
-    if ctx.needs_input_grad[1]:
-      gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
+    if WGRAD_SIDE_STREAM and x.is_cuda and not Profiler.enabled:
+      if ctx.needs_input_grad[1] and layer.weight.grad is None:
+        layer.weight.grad = torch.zeros_like(layer.weight)
+      patch_keep = getattr(layer, '_patch_cache', None)     # (the stem's patch matrix is dropped inside _wgrad)
+      main, side = torch.cuda.current_stream(x.device), side_stream(x.device)
+      side.wait_stream(main)                       # x and dy16 were produced on the main stream
+      _WS_SLOT[0] = 'side'
+      try:
+        with torch.cuda.stream(side):
+          layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh)
+          if ctx.needs_input_grad[1]:
+            layer.mask.apply_to(mw.dense_grad, out=layer.weight.grad.view(-1))
+      finally:
+        _WS_SLOT[0] = 'main'
+      _SIDE_KEEP.append((x, dy16, patch_keep))     # no reuse of these blocks before the join
+      mw.fresh = True
+    else:
+      _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
+      mw.fresh = True
+      if ctx.needs_input_grad[1]:
+        gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
     gb = None
     if ctx.has_bias and ctx.needs_input_grad[2]:
       gb = dy.float().reshape(-1, layer.out_channels).sum(0) if dy.dim() == 2 else \

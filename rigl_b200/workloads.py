@@ -249,8 +249,14 @@ class TrainHarness(object):
   # ---- CUDA-graph mode: the forward+backward and the inner optimizer step are captured once and
   # replayed (inter-kernel launch gaps and all host work disappear); the data-parallel
   # all-reduce, the schedule logic and the (rare) mask update stay eager between the replays.
-  def enable_cuda_graph(self, images, labels, warmup=3):
-    """Captures the step for fixed input shapes.  Returns False (and stays eager) if capture fails."""
+  def enable_cuda_graph(self, images, labels, warmup=3, overlap_wgrad=None):
+    """Captures the step for fixed input shapes.  Returns False (and stays eager) if capture fails.
+    overlap_wgrad: run the dense wgrad kernels on a forked stream inside the graph (layers.WGRAD_SIDE_STREAM);
+    default from RIGL_WGRAD_OVERLAP (on unless '0')."""
+    import os
+    if overlap_wgrad is None:
+      overlap_wgrad = os.environ.get('RIGL_WGRAD_OVERLAP', '1') != '0'
+    self._overlap = bool(overlap_wgrad)
     self._sx, self._sy = images.clone(), labels.clone()
     try:
       side = torch.cuda.Stream()
@@ -279,12 +285,18 @@ class TrainHarness(object):
     return self.graphed
 
   def _forward_backward(self, images, labels, set_to_none):
+    from . import layers
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
     self.inner.zero_grad(set_to_none=set_to_none)
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
-    loss.backward()
+    layers.WGRAD_SIDE_STREAM = bool(getattr(self, '_overlap', False))
+    try:
+      loss.backward()
+    finally:
+      layers.WGRAD_SIDE_STREAM = False
+      layers.join_side_streams()                # (no-op when nothing was forked)
     return loss
 
   def _graphed_step(self, images, labels):

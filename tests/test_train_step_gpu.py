@@ -158,3 +158,27 @@ def test_cuda_graph_mode_matches_eager():
   assert np.allclose(le, lg, rtol=2e-2, atol=2e-3)
   for a, b in zip(me, mg):
     assert a.sum() == b.sum()
+
+
+def test_cuda_graph_wgrad_side_stream_matches_serial_backward():
+  """In graph mode the dense wgrad kernels run on a forked stream (layers.WGRAD_SIDE_STREAM) next to the
+  BN-backward chain.  Every kernel is deterministic, so replaying the captured forward+backward must
+  reproduce the serial eager backward BIT FOR BIT (a missing dependency or a recycled buffer would not)."""
+  torch.manual_seed(3)
+  model = workloads.ResNet50(num_classes=10, device=DEV)
+  workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=3)
+  h = workloads.TrainHarness(model, lr=0.1)
+  x = torch.randn(8, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  y = torch.randint(0, 10, (8,), device=DEV)
+  h._forward_backward(x, y, set_to_none=False)            # serial reference (no fork: _overlap is unset)
+  torch.cuda.synchronize()
+  layers_ = model.registry.layers()
+  ref_dense = [l.masked_weights.dense_grad.clone() for l in layers_]
+  ref_grad = [l.weight.grad.clone() for l in layers_]
+  assert h.enable_cuda_graph(x, y, overlap_wgrad=True) and h._overlap
+  for _ in range(3):
+    h._g_fb.replay()
+    torch.cuda.synchronize()
+    for l, d, g in zip(layers_, ref_dense, ref_grad):
+      assert torch.equal(l.masked_weights.dense_grad, d), l.scope
+      assert torch.equal(l.weight.grad, g), l.scope
