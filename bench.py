@@ -258,7 +258,7 @@ def run_ours(args):
       'gpu_launches': int(launches),
       'mask_update_ms': mask_ms,
       'mask_update_algorithmic_GBps': 8.25 * total_w / mask_ms / 1e6,
-      'roofline': {'bound': 'tensor', 'kernel': 'k_igemm_kmajor / k_igemm_wgrad (all masked conv+linear launches)',
+      'roofline': {'bound': 'tensor', 'kernel': 'k_igemm_kmajor2 / k_igemm_wgrad / k_halo3x3_* (all masked conv+linear launches)',
                    'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved_tf / tf_peak,
                    'peak_source': peak_src + ' bf16_tflops_sustained',
                    'algorithmic_gflop_per_image': ALG_GFLOP_PER_IMAGE,
