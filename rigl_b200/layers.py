@@ -101,6 +101,38 @@ def side_stream(device):
   return st
 
 
+_PACKED_AHEAD = set()     # id(layer): operands already packed on the side stream for this step
+_PACK_JOIN = {}           # device -> True while the main stream has not yet waited for those packs
+
+
+def pack_ahead(layers):
+  """Packs the operands of `layers` on the side stream (they depend only on weights and masks, not on
+  activations), concurrently with whatever the caller's stream does next (the stem of the forward
+  pass); the first of these layers to run makes the main stream wait for all of them."""
+  layers = [l for l in layers if l.weight.is_cuda]
+  if not layers:
+    return
+  dev = layers[0].weight.device
+  main, side = torch.cuda.current_stream(dev), side_stream(dev)
+  side.wait_stream(main)                     # weights / masks were last written on the main stream
+  with torch.cuda.stream(side):
+    for l in layers:
+      l.pack()
+      _PACKED_AHEAD.add(id(l))
+  _PACK_JOIN[dev] = True
+
+
+def _pack_for_forward(layer):
+  if id(layer) in _PACKED_AHEAD:
+    _PACKED_AHEAD.discard(id(layer))
+    dev = layer.weight.device
+    if _PACK_JOIN.get(dev):
+      torch.cuda.current_stream(dev).wait_stream(side_stream(dev))
+      _PACK_JOIN[dev] = False
+    return
+  _timed('pack', layer, layer.pack)
+
+
 def join_side_streams():
   """The current stream of every device waits for the forked wgrad work; releases the kept tensors."""
   for dev, st in _SIDE.items():
@@ -138,7 +170,7 @@ class _MaskedConvFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, weight, bias, layer, out_f32):
-    _timed('pack', layer, layer.pack)
+    _pack_for_forward(layer)
     y = _timed('fprop', layer, lambda: layer._fprop(x, bias, out_f32))
     ctx.layer = layer
     ctx.save_for_backward(x)

@@ -257,6 +257,7 @@ class TrainHarness(object):
     if overlap_wgrad is None:
       overlap_wgrad = os.environ.get('RIGL_WGRAD_OVERLAP', '1') != '0'
     self._overlap = bool(overlap_wgrad)
+    self._pack_ahead = self._overlap and os.environ.get('RIGL_PACK_AHEAD', '1') != '0'
     self._sx, self._sy = images.clone(), labels.clone()
     try:
       side = torch.cuda.Stream()
@@ -289,6 +290,9 @@ class TrainHarness(object):
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
     self.inner.zero_grad(set_to_none=set_to_none)
+    if getattr(self, '_overlap', False) and getattr(self, '_pack_ahead', False):
+      # every layer but the first packs its operands on the side stream while the stem runs
+      layers.pack_ahead(self.model.registry.layers()[1:])
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
     layers.WGRAD_SIDE_STREAM = bool(getattr(self, '_overlap', False))
