@@ -182,6 +182,26 @@ RIGL_API int rigl_conv2d_wgrad_dense(const rigl_conv_desc* d, const void* x, con
  * runs as a masked dense layer over [pixels, k*k*cin] with the SAME HWIO weights and mask. */
 RIGL_API int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* out, int64_t out_pitch,
                               void* stream);
+/* EXPERIMENTAL (opt-in in the host mirror: layers.STEM_S2D_PATH; not yet validated on hardware).
+ * The 7x7 / stride-2 / 3-channel stem (conv2d_fixed_padding, resnet_model.py:619-629) without a
+ * patch matrix: rigl_stem_s2d_fold_input folds the zero-padded input 2x2 -> 16 channels
+ * ([N,(H+6)/2,(W+6)/2,16] bf16, rigl_stem_s2d_folded_bytes), the conv becomes a 4x4 stride-1 conv
+ * whose 16 taps are fed from one shared-memory halo tile; rigl_stem_s2d_pack_weights writes the
+ * [16 taps][cout][16] operand from the SAME HWIO weights + bitmap; _wgrad returns the dense
+ * [7,7,cin,cout] gradient.  Requires ksize 7, stride 2, pad 3, cin <= 3, cout <= 64, even extents,
+ * out_w <= 125. */
+RIGL_API int rigl_stem_s2d_supported(const rigl_conv_desc* d);
+RIGL_API size_t rigl_stem_s2d_folded_bytes(const rigl_conv_desc* d);
+RIGL_API size_t rigl_stem_s2d_packed_bytes(const rigl_conv_desc* d);
+RIGL_API size_t rigl_stem_s2d_workspace_bytes(const rigl_conv_desc* d);
+RIGL_API int rigl_stem_s2d_fold_input(const rigl_conv_desc* d, const void* x, void* xs, void* stream);
+RIGL_API int rigl_stem_s2d_pack_weights(const rigl_conv_desc* d, const float* w_hwio,
+                                        const uint32_t* mask_bits, void* packed, void* stream);
+RIGL_API int rigl_stem_s2d_fprop(const rigl_conv_desc* d, const void* xs, const void* packed, void* y,
+                                 void* stream);
+RIGL_API int rigl_stem_s2d_wgrad(const rigl_conv_desc* d, const void* xs, const void* dy, float* dw,
+                                 float beta, void* ws, size_t ws_bytes, void* stream);
+
 /* Small-Cin convs (cin <= 8, ksize <= 8: the 7x7x3 stem, resnet_model.py:620-633) WITHOUT a
  * patch matrix: the input is copied once into a zero-bordered 8-channel buffer `xp`
  * (rigl_smallc_padded_bytes); window tensor maps with a W stride of `stride` pixels then feed

@@ -56,6 +56,14 @@ SIGNATURES = {
     'rigl_masked_conv2d_dgrad': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
     'rigl_conv2d_wgrad_dense': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
     'rigl_im2col_nhwc': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _i64, _vp]),
+    'rigl_stem_s2d_supported': (C.c_int, [C.POINTER(ConvDesc)]),
+    'rigl_stem_s2d_folded_bytes': (_sz, [C.POINTER(ConvDesc)]),
+    'rigl_stem_s2d_packed_bytes': (_sz, [C.POINTER(ConvDesc)]),
+    'rigl_stem_s2d_workspace_bytes': (_sz, [C.POINTER(ConvDesc)]),
+    'rigl_stem_s2d_fold_input': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    'rigl_stem_s2d_pack_weights': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    'rigl_stem_s2d_fprop': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    'rigl_stem_s2d_wgrad': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
     'rigl_smallc_supported': (C.c_int, [C.POINTER(ConvDesc)]),
     'rigl_smallc_padded_bytes': (_sz, [C.POINTER(ConvDesc)]),
     'rigl_smallc_packed_bytes': (_sz, [C.POINTER(ConvDesc)]),

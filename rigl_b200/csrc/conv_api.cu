@@ -53,6 +53,56 @@ extern "C" int rigl_im2col_nhwc(const rigl_conv_desc* d, const void* x, void* ou
 }
 
 // ---- small-Cin (stem) convs: zero-bordered 8-channel input + window tensor maps ----
+// ---- space-to-depth stem (experimental, see stem_s2d.cuh) ----
+extern "C" int rigl_stem_s2d_supported(const rigl_conv_desc* d) {
+  ConvGeom g;
+  if (geom_from_desc(d, &g) != RIGL_OK) return 0;
+  return s2d_supported(g) && !force_simt() ? 1 : 0;
+}
+extern "C" size_t rigl_stem_s2d_folded_bytes(const rigl_conv_desc* d) {
+  ConvGeom g;
+  return geom_from_desc(d, &g) == RIGL_OK ? s2d_folded_bytes(g) : 0;
+}
+extern "C" size_t rigl_stem_s2d_packed_bytes(const rigl_conv_desc* d) {
+  ConvGeom g;
+  return geom_from_desc(d, &g) == RIGL_OK ? s2d_packed_bytes(g) : 0;
+}
+extern "C" size_t rigl_stem_s2d_workspace_bytes(const rigl_conv_desc* d) {
+  ConvGeom g;
+  return geom_from_desc(d, &g) == RIGL_OK ? s2d_workspace_bytes(g) : 0;
+}
+extern "C" int rigl_stem_s2d_fold_input(const rigl_conv_desc* d, const void* x, void* xs, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(x && xs && s2d_supported(g) && aligned16(xs), "rigl_stem_s2d_fold_input: bad arguments");
+  return s2d_fold(g, x, xs, (cudaStream_t)stream);
+}
+extern "C" int rigl_stem_s2d_pack_weights(const rigl_conv_desc* d, const float* w_hwio, const uint32_t* mask_bits,
+                                          void* packed, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(w_hwio && mask_bits && packed && s2d_supported(g), "rigl_stem_s2d_pack_weights: bad arguments");
+  return s2d_pack(g, w_hwio, mask_bits, packed, (cudaStream_t)stream);
+}
+extern "C" int rigl_stem_s2d_fprop(const rigl_conv_desc* d, const void* xs, const void* packed, void* y,
+                                   void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(xs && packed && y && s2d_supported(g), "rigl_stem_s2d_fprop: bad arguments");
+  return s2d_fprop(g, xs, packed, y, (cudaStream_t)stream);
+}
+extern "C" int rigl_stem_s2d_wgrad(const rigl_conv_desc* d, const void* xs, const void* dy, float* dw, float beta,
+                                   void* ws, size_t ws_bytes, void* stream) {
+  ConvGeom g;
+  int rc = geom_from_desc(d, &g);
+  if (rc != RIGL_OK) return rc;
+  RIGL_REQUIRE(xs && dy && dw && s2d_supported(g), "rigl_stem_s2d_wgrad: bad arguments");
+  return s2d_wgrad(g, xs, dy, dw, beta, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int rigl_smallc_supported(const rigl_conv_desc* d) {
   ConvGeom g;
   if (geom_from_desc(d, &g) != RIGL_OK) return 0;

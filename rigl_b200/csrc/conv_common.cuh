@@ -64,6 +64,16 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
              size_t ws_bytes, cudaStream_t s);
 
 // small-Cin (stem) path (igemm_tc.cu)
+// Space-to-depth stem (stem_s2d.cuh) -- experimental, opt-in
+bool s2d_supported(const ConvGeom& g);
+size_t s2d_folded_bytes(const ConvGeom& g);
+size_t s2d_packed_bytes(const ConvGeom& g);
+size_t s2d_workspace_bytes(const ConvGeom& g);
+int s2d_fold(const ConvGeom& g, const void* x, void* xs, cudaStream_t s);
+int s2d_pack(const ConvGeom& g, const float* w, const uint32_t* bits, void* packed, cudaStream_t s);
+int s2d_fprop(const ConvGeom& g, const void* xs, const void* packed, void* y, cudaStream_t s);
+int s2d_wgrad(const ConvGeom& g, const void* xs, const void* dy, float* dw, float beta, void* ws, size_t ws_bytes,
+              cudaStream_t s);
 bool smallc_supported(const ConvGeom& g);
 size_t smallc_padded_bytes(const ConvGeom& g);
 size_t smallc_packed_bytes(const ConvGeom& g);

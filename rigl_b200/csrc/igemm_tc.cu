@@ -926,15 +926,15 @@ static int ensure_driver() {
 }
 
 // bf16 tensor map over `rank` dims (dim 0 innermost, contiguous), 128B swizzle, zero OOB fill.
-static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+static int make_tmap_swz(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, CUtensorMapSwizzle swz) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
-                        gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r,
@@ -944,6 +944,10 @@ static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_
     return RIGL_ERR_DRIVER;
   }
   return RIGL_OK;
+}
+static int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+  return make_tmap_swz(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // Activation view (C, W_r, H_r, N) of an NHWC tensor sub-sampled by `s` at parity (rh, rw).
@@ -1009,6 +1013,7 @@ static int wgrad_bn_tile(const ConvGeom& g) {
 }
 
 #include "halo3x3.cuh"
+#include "stem_s2d.cuh"
 
 size_t tc_workspace_bytes(const ConvGeom& g) {
   if (!tc_supported(g, 2)) return 0;

@@ -38,6 +38,8 @@ def _bn_partial_rows():
 
 
 STEM_WINDOW_PATH = False     # route small-Cin convs through the window-tensor-map kernels
+STEM_S2D_PATH = False        # EXPERIMENTAL (not yet validated on hardware): space-to-depth halo kernels for the
+                             # 7x7/2 3-channel stem (csrc/stem_s2d.cuh)
 
 
 class Profiler(object):
@@ -284,6 +286,11 @@ class SparseConv2d(_MaskedLayer):
     if self.smallc_mode:
       self.packed_smallc = torch.zeros(k * int(units) * 64 * 2, dtype=torch.uint8, device=device)
     self._use_smallc = False
+    self.s2d_mode = bool(STEM_S2D_PATH and self.patch_mode and k == 7 and s == 2 and int(in_channels) <= 3 and
+                         int(units) <= 64 and int(units) % 8 == 0 and padding == 'FIXED')
+    if self.s2d_mode:
+      self.packed_s2d = torch.zeros(16 * int(units) * 32, dtype=torch.uint8, device=device)
+    self._use_s2d = False
     self.collect_bn_stats = False   # set by the model when a FusedBatchNormReLU consumes this output
     self.bn_partial = None
 
@@ -292,6 +299,11 @@ class SparseConv2d(_MaskedLayer):
       _cabi.check(_cabi.lib().rigl_pack_masked_weights(
           self.weight.data_ptr(), self.mask.bits.data_ptr(), 1, self._kdim, self._cout,
           self.packed_patch.data_ptr(), _cabi.stream_ptr()), 'rigl_pack_masked_weights')
+      if self.s2d_mode:
+        d = self._desc(1, 16, 16)
+        _cabi.check(_cabi.lib().rigl_stem_s2d_pack_weights(
+            d, self.weight.data_ptr(), self.mask.bits.data_ptr(), self.packed_s2d.data_ptr(),
+            _cabi.stream_ptr()), 'rigl_stem_s2d_pack_weights')
       if self.smallc_mode:
         d = self._desc(1, max(self.ksize, 8), max(self.ksize, 8))
         _cabi.check(_cabi.lib().rigl_smallc_pack_weights(
@@ -354,6 +366,15 @@ class SparseConv2d(_MaskedLayer):
     y = torch.empty((n, self._cout, d.out_h, d.out_w), dtype=torch.bfloat16, device=x.device,
                     memory_format=torch.channels_last)
     packed, src = self.packed, x
+    self._use_s2d = bool(self.s2d_mode and _cabi.lib().rigl_stem_s2d_supported(d))
+    if self._use_s2d:
+      xs = torch.empty(int(_cabi.lib().rigl_stem_s2d_folded_bytes(d)), dtype=torch.uint8, device=x.device)
+      _cabi.check(_cabi.lib().rigl_stem_s2d_fold_input(d, x.data_ptr(), xs.data_ptr(), _cabi.stream_ptr()),
+                  'rigl_stem_s2d_fold_input')
+      _cabi.check(_cabi.lib().rigl_stem_s2d_fprop(d, xs.data_ptr(), self.packed_s2d.data_ptr(), y.data_ptr(),
+                                                  _cabi.stream_ptr()), 'rigl_stem_s2d_fprop')
+      self._patch_cache = xs
+      return y
     self._use_smallc = bool(self.smallc_mode and _cabi.lib().rigl_smallc_supported(d))
     if self._use_smallc:
       try:
@@ -405,6 +426,13 @@ class SparseConv2d(_MaskedLayer):
   def _wgrad(self, x, dy, out, accumulate):
     n, c, h, w = x.shape
     d, src = self._desc(n, h, w), x
+    if self._use_s2d and getattr(self, '_patch_cache', None) is not None:
+      xs, self._patch_cache = self._patch_cache, None
+      ws = _workspace(x.device, _cabi.lib().rigl_stem_s2d_workspace_bytes(d))
+      _cabi.check(_cabi.lib().rigl_stem_s2d_wgrad(
+          d, xs.data_ptr(), dy.data_ptr(), out.data_ptr(), 1.0 if accumulate else 0.0, ws.data_ptr(),
+          ws.numel(), _cabi.stream_ptr()), 'rigl_stem_s2d_wgrad')
+      return
     if self._use_smallc and getattr(self, '_patch_cache', None) is not None:
       xp, self._patch_cache = self._patch_cache, None
       ws = _workspace(x.device, _cabi.lib().rigl_smallc_workspace_bytes(d))
