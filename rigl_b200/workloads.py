@@ -255,7 +255,11 @@ class TrainHarness(object):
     default from RIGL_WGRAD_OVERLAP (on unless '0')."""
     import os
     if overlap_wgrad is None:
-      overlap_wgrad = os.environ.get('RIGL_WGRAD_OVERLAP', '1') != '0'
+      # default: on for the single-GPU step (the validated configuration); with data parallelism the
+      # serial backward is kept until the fork has been measured together with the all-reduce
+      # (RIGL_WGRAD_OVERLAP=1 forces it on, =0 off)
+      env = os.environ.get('RIGL_WGRAD_OVERLAP')
+      overlap_wgrad = (env != '0') if (env is not None or self.dp is None) else False
     self._overlap = bool(overlap_wgrad)
     self._pack_ahead = self._overlap and os.environ.get('RIGL_PACK_AHEAD', '1') != '0'
     self._sx, self._sy = images.clone(), labels.clone()
