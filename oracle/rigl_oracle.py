@@ -318,6 +318,62 @@ def set_mask_update(mask, weights, random_grow_scores, drop_fraction, noise=None
   return get_update_op(sd, random_grow_scores, mask, weights, drop_fraction, slots=slots)
 
 
+# --------------------------------------------------------------------------
+# rigl/sparse_optimizers.py -- the remaining optimizers on the same select primitive
+# (oracle first; the B200 product path for them is round-2 work)
+# --------------------------------------------------------------------------
+def momentum_ema_update(ema, masked_grad, momentum):
+  """SparseMomentumOptimizer._before_apply_gradients (sparse_optimizers.py:172,195-197):
+  tf.train.ExponentialMovingAverage(decay=momentum).apply on a Tensor: the shadow starts at zero and
+  follows shadow <- decay*shadow + (1-decay)*value; `average()` returns that shadow -- the reference's
+  own test pins exactly this trajectory (sparse_optimizers_test.py:276-295)."""
+  return (F32(momentum) * ema.astype(F32) + F32(1. - momentum) * masked_grad.astype(F32)).astype(F32)
+
+
+def momentum_mask_update(mask, weights, ema_grad, drop_fraction, noise=None, slots=()):
+  """SparseMomentumOptimizer.generic_mask_update (sparse_optimizers.py:199-214): drop by
+  |mask*w| (+noise), grow by |EMA of the dense gradient|; new connections zero-initialised."""
+  sd = np.abs(mask.astype(F32) * weights.astype(F32))
+  if noise is not None:
+    sd = (sd + noise.astype(F32)).astype(F32)
+  return get_update_op(sd, np.abs(ema_grad.astype(F32)), mask, weights, drop_fraction, slots=slots)
+
+
+def top_k_keep_mask(score, sparsity):
+  """snip_fn / dnw_fn (sparse_optimizers.py:293-315 and 427-452): keep the n_keep =
+  n_total - get_n_zeros(n_total, sparsity) highest scores; tf.nn.top_k over the WHOLE flattened
+  array, so equal scores keep the lower flat index."""
+  flat = score.astype(F32).ravel()
+  n_total = flat.size
+  n_keep = n_total - get_n_zeros(n_total, sparsity)
+  order = _top_k_indices_all(flat)
+  mask = np.zeros(n_total, F32)
+  mask[order[:n_keep]] = 1
+  return mask.reshape(score.shape)
+
+
+def snip_mask(grad, weights, sparsity):
+  """SparseSnipOptimizer.snip_fn: score = |g * w| (sparse_optimizers.py:293)."""
+  return top_k_keep_mask(np.abs(grad.astype(F32) * weights.astype(F32)), sparsity)
+
+
+def dnw_mask(weights, sparsity):
+  """SparseDNWOptimizer.dnw_fn: score = |w| of the weights AFTER the optimizer step (:408-431)."""
+  return top_k_keep_mask(np.abs(weights.astype(F32)), sparsity)
+
+
+class SnipSim(object):
+  """Control flow of SparseSnipOptimizer.apply_gradients (sparse_optimizers.py:317-337): the first
+  call at global_step 0 snips (no weight update, step counter NOT incremented), every later call is a
+  plain optimizer step."""
+
+  def __init__(self):
+    self.is_snipped = False
+
+  def is_snip_iter(self, global_step):
+    return global_step == 0 and not self.is_snipped
+
+
 def tf2_generic_mask_update(mask, weights, score_drop, score_grow, drop_fraction):
   """Independent second statement: rigl/rigl_tf2/mask_updaters.py:99-154.
 
