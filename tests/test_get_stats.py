@@ -90,3 +90,22 @@ def test_width_scaling_and_layer_spec_from_shapes():
   assert f2 == c1(3, 32) + c1(32, 32) + 2 * 32 * 10
   with pytest.raises(ValueError):
     su.LayerSpec('pool', 'x', (1,))
+
+
+def test_get_compressed_fc():
+  """mnist_train_eval.py:165-189 on a hand-checkable 4-3-2 network."""
+  m0 = np.array([[1, 0, 0],      # input 0 -> unit 0
+                 [0, 0, 0],      # input 1 dead
+                 [0, 0, 1],      # input 2 -> unit 2
+                 [1, 0, 1]])     # input 3 -> units 0, 2     (unit 1 has no incoming edge)
+  m1 = np.array([[1, 0],         # unit 0 -> out 0
+                 [1, 1],         # unit 1 (dead upstream) -> both outputs
+                 [0, 0]])        # unit 2 has no outgoing edge
+  keep0, keep1 = m0.copy(), m1.copy()
+  sp, sizes = su.get_compressed_fc([m0, m1])
+  assert sizes == [3, 1, 1]                                  # 3 live inputs, only unit 0 survives, out 1 loses its only edge
+  assert sp == [1.0 / 3.0, 0.0]
+  assert (m0 == keep0).all() and (m1 == keep1).all()         # inputs untouched
+  # a dense network is returned unchanged
+  sp, sizes = su.get_compressed_fc([np.ones((5, 4)), np.ones((4, 3))])
+  assert sp == [0.0, 0.0] and sizes == [5, 4, 3]
