@@ -13,13 +13,16 @@ Parity pinning status (see DESIGN.md "Oracle"):
     against the known-answer counts in rigl/sparse_utils_test.py:47-55.
   * schedule / step semantics: PINNED against the explicit vectors in
     rigl/sparse_optimizers_test.py:85,108,349-352.
-  * drop/grow mask update (`get_update_op`): restates
-    rigl/sparse_optimizers_base.py:276-343 with TF `top_k` == stable descending
-    argsort.  The reference holds no golden mask tensors (only invariants,
-    which tests/test_oracle.py asserts) and TensorFlow is not installable
-    here => "parity unpinned" for exact indices beyond those invariants and a
-    cross-check against the independent TF2 statement
-    rigl/rigl_tf2/mask_updaters.py:99-154 restated in `tf2_generic_mask_update`.
+  * drop/grow mask update (`get_update_op`, `rigl_mask_update`, grow tensors, slot reset): restates
+    rigl/sparse_optimizers_base.py:276-353,523-564 with TF `top_k` == stable descending argsort.
+    PINNED TO THE REFERENCE'S CODE, TF PRIMITIVES STUBBED: tools/make_golden_update_op.py imports
+    the reference module unmodified and EXECUTES its `_get_update_op` / `generic_mask_update` /
+    `reset_momentum` / `get_grow_tensor` over a numpy-backed stand-in for the ~20 TF ops they call;
+    tests/test_update_op_golden.py checks masks, weights and slots bit-for-bit on 13 cases (ties,
+    reinit, grad_scale / grad_sign grow, accumulator scale, conv shapes).  What remains unpinned is
+    only the behaviour of the TF primitives themselves (top_k tie order, float->int cast), taken
+    from their documentation; TensorFlow is not installable here.  Additional cross-check: the
+    independent TF2 statement rigl/rigl_tf2/mask_updaters.py:99-154 (`tf2_generic_mask_update`).
   * masked conv / linear numerics: third-party (tf.contrib.model_pruning,
     un-vendored); restated as y = op(x, mask*w).  "parity unpinned".
 
