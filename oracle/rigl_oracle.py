@@ -327,10 +327,12 @@ def set_mask_update(mask, weights, random_grow_scores, drop_fraction, noise=None
 # --------------------------------------------------------------------------
 def momentum_ema_update(ema, masked_grad, momentum):
   """SparseMomentumOptimizer._before_apply_gradients (sparse_optimizers.py:172,195-197):
-  tf.train.ExponentialMovingAverage(decay=momentum).apply on a Tensor: the shadow starts at zero and
-  follows shadow <- decay*shadow + (1-decay)*value; `average()` returns that shadow -- the reference's
-  own test pins exactly this trajectory (sparse_optimizers_test.py:276-295)."""
-  return (F32(momentum) * ema.astype(F32) + F32(1. - momentum) * masked_grad.astype(F32)).astype(F32)
+  tf.train.ExponentialMovingAverage(decay=momentum).apply on a Tensor: the shadow starts at zero (no
+  zero-debias: the constructor default) and is updated by moving_averages.assign_moving_average,
+  shadow -= (shadow - value) * (1 - decay), in float32; `average()` returns that shadow.  The
+  reference's own test pins this trajectory (sparse_optimizers_test.py:276-295)."""
+  e, g = ema.astype(F32), masked_grad.astype(F32)
+  return (e - (e - g) * F32(1.0 - momentum)).astype(F32)
 
 
 def momentum_mask_update(mask, weights, ema_grad, drop_fraction, noise=None, slots=()):

@@ -197,3 +197,56 @@ def test_rigl_update_through_public_api_matches_oracle():
     assert l.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes()
     assert optim.state[l.weight]['momentum_buffer'].cpu().numpy().tobytes() == want['slots'][0].tobytes()
     assert l.mask.count_ones() == int(s['mask'].sum())
+
+
+# ---- SparseMomentumOptimizer (sparse_optimizers.py:126-214).  The host logic is covered on the CPU
+# (tests/test_oracle_other_optimizers.py); these two run the real layers + select kernels and were
+# written after the round's GPU budget was spent, so they are gated until their first validated run.
+_EXPERIMENTAL = __import__('os').environ.get('RIGL_TEST_EXPERIMENTAL') == '1'
+
+
+@pytest.mark.skipif(not _EXPERIMENTAL, reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
+@pytest.mark.parametrize('n_inp,n_out,momentum', [(3, 4, 0.5), (5, 2, 0.), (2, 5, 1.)])
+def test_momentum_update(n_inp, n_out, momentum):
+  """sparse_optimizers_test.py:276-295 (testMomentumUpdate)."""
+  pruning.reset_default_registry()
+  layer = SparseLinear(n_inp, n_out, name='fully_connected', device=DEV, out_dtype=torch.float32)
+  optim = torch.optim.SGD(layer.parameters(), lr=0.1)
+  gs = GlobalStep(0)
+  so = sparse_optimizers.SparseMomentumOptimizer(optim, 1, 4, 2, drop_fraction=0.5, momentum=momentum)
+  current = np.zeros((n_inp, n_out))
+  for _ in range(6):
+    x = torch.ones(1, n_inp, device=DEV)
+    y = layer(x)
+    loss = (y * torch.arange(y.numel(), device=DEV, dtype=y.dtype).reshape(y.shape)).sum()
+    so.minimize(loss, gs)
+    current = current * momentum + (1 - momentum) * np.arange(n_out)
+    got = so.ema_average(layer.weight).view(n_inp, n_out).cpu().numpy()
+    assert np.array_equal(got, current.astype(np.float32))
+
+
+@pytest.mark.skipif(not _EXPERIMENTAL, reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
+def test_momentum_mask_update_matches_oracle():
+  pruning.reset_default_registry()
+  torch.manual_seed(2)
+  rng = np.random.RandomState(2)
+  layer = SparseLinear(64, 48, name='layer1', device=DEV, out_dtype=torch.float32)
+  layer.mask.assign(orc.get_mask_random_numpy((64, 48), 0.8, rng))
+  optim = torch.optim.SGD(layer.parameters(), lr=0.05)
+  so = sparse_optimizers.SparseMomentumOptimizer(optim, 0, 1000, 5, drop_fraction=0.3, momentum=0.9)
+  gs = GlobalStep(1)
+  x = torch.randn(32, 64, device=DEV)
+  t = torch.randn(32, 48, device=DEV)
+  loss_fn = lambda: ((layer(x) - t) ** 2).mean()
+  for _ in range(4):                                    # steps 1..4: plain steps, EMA accumulates
+    so.minimize(loss_fn(), gs)
+  assert gs.value == 5
+  gv = so.compute_gradients(loss_fn())
+  mask0, w0 = layer.mask.numpy(), layer.weight.detach().cpu().numpy().copy()
+  ema_before = so.ema_average(layer.weight).cpu().numpy().copy()
+  g = layer.masked_weights.dense_grad.cpu().numpy().copy()
+  so.apply_gradients(gv, gs)                            # SET-style: step, then the update on step 6? no: freq 5
+  # (SET semantics, base.apply_gradients: the optimizer step runs first, then the mask update if due)
+  ema_after = orc.momentum_ema_update(ema_before, g, 0.9)
+  assert np.array_equal(so.ema_average(layer.weight).cpu().numpy(), ema_after)
+  assert layer.mask.count_ones() == int(mask0.sum())

@@ -76,3 +76,27 @@ def test_dnw_keeps_the_largest_magnitudes(n_inp, n_out, sparsity):
   w2.ravel()[np.argmax(np.abs(w))] = 0.
   m2 = orc.dnw_mask(w2, sparsity)
   assert m2.ravel()[np.argmax(np.abs(w))] == 0 and m2.sum() == m.sum()
+
+
+@pytest.mark.parametrize('n_inp,n_out,momentum', [(3, 4, 0.5), (5, 2, 0.), (2, 5, 1.), (4, 4, 0.9)])
+def test_momentum_optimizer_host_logic_matches_oracle(n_inp, n_out, momentum):
+  """The product class' EMA bookkeeping (rigl_b200.sparse_optimizers.SparseMomentumOptimizer) on CPU
+  tensors: same trajectory as the oracle / the reference's testMomentumUpdate; the grow score handed
+  to the select kernels is that EMA."""
+  import torch
+  from rigl_b200.sparse_optimizers import SparseMomentumOptimizer
+
+  class W(object):
+    name = 'layer/weights:0'
+  w = torch.nn.Parameter(torch.zeros(n_inp, n_out))
+  opt = SparseMomentumOptimizer(torch.optim.SGD([w], lr=0.1), 1, 4, 2, drop_fraction=0.5, momentum=momentum)
+  g = torch.arange(n_out, dtype=torch.float32).repeat(n_inp, 1).contiguous().view(-1)
+  opt.get_weights = lambda: [W]
+  opt.get_masked_weights = lambda: []
+  opt.set_masked_grads([g], [W])
+  ema = np.zeros(n_inp * n_out, np.float32)
+  for _ in range(6):
+    opt._before_apply_gradients(None)
+    ema = orc.momentum_ema_update(ema, g.numpy(), momentum)
+    assert np.array_equal(opt.ema_average(W).numpy(), ema)
+    assert opt._score_grow_for(None, W) is opt.ema_average(W)
