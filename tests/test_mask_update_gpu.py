@@ -256,3 +256,39 @@ def test_idempotent_count_and_repeatability():
     outs.append(mv.bits.clone())
     assert mv.count_ones() == int(ly['mask'].sum())
   assert torch.equal(outs[0], outs[1])
+
+
+# ---- the CUDA update on the exact inputs of the golden vectors produced by executing the reference's
+# `_get_update_op` / `generic_mask_update` (tools/make_golden_update_op.py).  The oracle already matches
+# those vectors bit-for-bit on the CPU (tests/test_update_op_golden.py); this closes the loop on the
+# device.  Written after the round's GPU budget was spent: gated until its first validated run.
+import json as _json
+import os as _os
+
+_GOLD_PATH = _os.path.join(_os.path.dirname(__file__), 'golden', 'update_op_golden.json')
+with open(_GOLD_PATH) as _f:
+  _GOLD = _json.load(_f)
+
+
+def _gdec(e):
+  return None if e is None else np.frombuffer(bytes.fromhex(e['hex']), dtype=np.dtype(e['dtype'])).reshape(e['shape']).copy()
+
+
+@pytest.mark.skipif(_os.environ.get('RIGL_TEST_EXPERIMENTAL') != '1',
+                    reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
+@pytest.mark.parametrize('case', _GOLD['cases'], ids=[c['tag'] for c in _GOLD['cases']])
+def test_cuda_update_on_reference_executed_golden_inputs(case):
+  i = case['in']
+  rigl = case['optimizer'] == 'SparseRigLOptimizerBase'
+  g = _gdec(i['dense_grad']) if rigl else _gdec(i['score_grow'])
+  layer = dict(mask=_gdec(i['mask']), w=_gdec(i['weights']), g=g, slots=[_gdec(s) for s in i['slots']])
+  if i['noise'] is not None:
+    layer['noise'] = _gdec(i['noise'])
+  mode, div = _cabi.GROW_ZEROS, 1.0
+  if case['grow_init'].startswith('grad_scale'):
+    mode, div = _cabi.GROW_GRAD_SCALE, orc.extract_number(case['grow_init'])
+  elif case['grow_init'].startswith('grad_sign'):
+    mode, div = _cabi.GROW_GRAD_SIGN, orc.extract_number(case['grow_init'])
+  _run_case([layer], np.float32(float.fromhex(case['drop_fraction'])), grow_mode=mode, grow_divisor=div,
+            acc_scale=float(np.float32(float.fromhex(case['initial_acc_scale']))), reinit=case['reinit_when_same'],
+            check_stats=False)
