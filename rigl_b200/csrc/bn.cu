@@ -13,6 +13,9 @@
 // Every kernel moves 16-byte vectors (8 channels) per thread with the channel dimension
 // innermost, so global traffic is fully coalesced; reductions go registers -> smem ->
 // per-block partials -> a tiny finalize kernel (fixed order: deterministic).
+// Tensors that fit in L2 take the single-launch variants (k_bn_fwd_fused / k_bn_bwd_fused: the
+// same three phases behind two grid barriers); rigl_bn_backward2 also sums the two gradients of a
+// forked block output inside the reduce pass.
 #include <cuda_bf16.h>
 
 #include "common.cuh"

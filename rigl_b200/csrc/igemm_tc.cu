@@ -6,7 +6,7 @@
 // Wm = mask * W is produced once per step by pack.cu; its per-tile survivor counts
 // gate the weight-tile loads (an all-zero 64x64 weight tile costs no TMA and no MMA).
 //
-// No im2col buffer exists anywhere: an M tile is a BOX of 128 output pixels
+// No im2col buffer (except the 3-channel stem's patch matrix, conv_simt.cu): an M tile is a BOX of 128 output pixels
 // (bw x bh x bn over width, height, batch) and, for filter tap (kh,kw), the A
 // operand is the same box shifted by the tap offset, fetched by ONE 4-D TMA
 // (cp.async.bulk.tensor.4d) whose out-of-bounds zero fill implements the padding.
@@ -15,11 +15,16 @@
 // TMA boxes + tcgen05.mma with fp32 accumulators in TMEM.
 //
 // Kernel organisation (persistent, one CTA per SM, 192 threads):
-//   warp 0    : TMA producer (one elected lane)      smem ring, full/empty mbarriers
-//   warp 1    : TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, M=128
-//   warps 2-5 : epilogue: tcgen05.ld 32x32b -> registers -> bf16/fp32 global stores,
-//               double-buffered accumulators so the epilogue of tile i overlaps the
-//               main loop of tile i+1.
+//   warp 0    : TMA producer (converged warp, one elect.sync lane issues)   smem ring, full/empty mbarriers
+//   warp 1    : TMEM allocator + MMA issuer (same pattern): tcgen05.mma kind::f16, M = 128 per CTA
+//   warps 2-5 : epilogue: tcgen05.ld 32x32b -> bf16 -> swizzled smem slab -> TMA store (or direct
+//               fp32/bias stores), double-buffered accumulators so the epilogue of tile i overlaps
+//               the main loop of tile i+1.
+// Variants: k_igemm_kmajor (one CTA per tile, optional 2-CTA weight multicast, optional fused BN
+// statistics), k_igemm_kmajor2 (default for fprop/dgrad: CTA pair, tcgen05 cta_group::2, M = 256),
+// k_igemm_wgrad, and -- textually included below -- halo3x3.cuh (3x3/s1 layers with <= 64 channels:
+// one smem halo tile feeds all nine taps) and stem_s2d.cuh (experimental).  Measured limits that
+// shape these kernels (TMA ingest 54 B/clk/SM, cycles per MMA by N): DESIGN.md 3.2 / 3.7.
 // fprop/dgrad use K-major operands; wgrad reduces over pixels, so both operands are
 // MN-major views of the NHWC tensors (no transposes are materialised) and the
 // pixel range is split across CTAs (deterministic two-pass split-K).
