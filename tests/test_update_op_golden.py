@@ -50,3 +50,16 @@ def test_golden_covers_both_optimizers_and_the_tie_rule():
   tags = {c['tag'] for c in GOLD['cases']}
   assert {'set_ties', 'rigl_ties', 'rigl_generic', 'rigl_grad_scale', 'rigl_grad_sign', 'set_reinit'} <= tags
   assert GOLD['generator'] == 'tools/make_golden_update_op.py'
+
+
+def test_static_cases_keep_the_mask_and_reinitialise_dropped_weights():
+  """SparseStaticOptimizer (sparse_optimizers.py:109-123): grow score = mask, reinit_when_same=True --
+  the connectivity never changes, the dropped (weakest) connections restart from the grow tensor."""
+  for case in GOLD['cases']:
+    if not case['tag'].startswith('static'):
+      continue
+    m0, w0 = _dec(case['in']['mask']), _dec(case['in']['weights'])
+    m1, w1 = _dec(case['out']['mask']), _dec(case['out']['weights'])
+    assert np.array_equal(m0, m1)
+    changed = w0 != w1
+    assert changed.any() and (w1[changed] == 0).all() and (m0[changed] == 1).all()

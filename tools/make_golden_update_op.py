@@ -169,7 +169,7 @@ def main():
   rng = np.random.RandomState(20260923)
 
   def run(tag, cls, shape, sparsity, drop_fraction, grow_init='zeros', reinit=False, ties=False, acc_scale=0.,
-          n_slots=1, via_generic=False):
+          n_slots=1, via_generic=False, static=False):
     n = int(np.prod(shape))
     mask0 = (rng.rand(*shape) >= sparsity).astype(F32)
     if ties:                                         # many equal scores: exercises the top_k tie rule
@@ -207,6 +207,8 @@ def main():
     else:
       sd = (np.abs(mask0 * w0)).astype(F32)
       sg = np.abs(g0).astype(F32) if cls is ref.SparseRigLOptimizerBase else rng.rand(*shape).astype(F32)
+      if static:                                     # SparseStaticOptimizer.generic_mask_update: score_grow = mask
+        sg = mask0.copy()
       cls._get_update_op(me, sd, sg, mask, weights, reinit_when_same=reinit)
     cases.append({
         'tag': tag, 'optimizer': cls.__name__, 'shape': list(shape), 'drop_fraction': float(F32(drop_fraction)).hex(),
@@ -227,6 +229,8 @@ def main():
   run('set_conv_shape', SET, (3, 3, 4, 8), 0.8, 0.3, n_slots=2)
   run('set_drop_all', SET, (4, 5), 0.5, 1.0)
   run('set_drop_none', SET, (4, 5), 0.5, 0.0)
+  run('static_basic', SET, (6, 7), 0.5, 0.4, reinit=True, static=True)
+  run('static_ties', SET, (8, 8), 0.6, 0.5, reinit=True, ties=True, static=True, n_slots=2)
   run('rigl_basic', RIGL, (6, 7), 0.5, 0.3)
   run('rigl_ties', RIGL, (8, 8), 0.7, 0.5, ties=True)
   run('rigl_grad_scale', RIGL, (3, 3, 4, 8), 0.8, 0.3, grow_init='grad_scale_2', acc_scale=0.5)
