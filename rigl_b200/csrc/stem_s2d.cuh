@@ -1,5 +1,5 @@
-// EXPERIMENTAL (opt-in, layers.STEM_S2D_PATH; written at the end of round 1 and NOT YET RUN on
-// hardware -- the default stem path is the patch matrix + GEMM).  Design: DESIGN.md 3.7.
+// Space-to-depth stem kernels (layers.STEM_S2D_PATH, default on; validated on B200 in round 2 by
+// tools/umma_sw32_probe.cu and tests/test_conv_gpu.py::test_conv_stem_s2d_path).  Design: DESIGN.md 3.7.
 //
 // The 7x7 / stride-2 / 3-channel stem without a patch matrix.  The zero-padded input is folded
 // 2x2 -> channels ("space to depth"): xs[n, hs, ws, (dy*2+dx)*3 + c] = xpad[n, 2hs+dy, 2ws+dx, c],

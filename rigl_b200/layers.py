@@ -38,8 +38,11 @@ def _bn_partial_rows():
 
 
 STEM_WINDOW_PATH = False     # route small-Cin convs through the window-tensor-map kernels
-STEM_S2D_PATH = False        # EXPERIMENTAL (not yet validated on hardware): space-to-depth halo kernels for the
-                             # 7x7/2 3-channel stem (csrc/stem_s2d.cuh)
+import os as _os
+# space-to-depth halo kernels for the 7x7/2 3-channel stem (csrc/stem_s2d.cuh): validated on
+# B200 at the start of round 2 (tools/umma_sw32_probe.cu + tests/test_conv_gpu.py::test_conv_stem_s2d_path);
+# RIGL_STEM_S2D=0 falls back to the patch-matrix (im2col) stem
+STEM_S2D_PATH = _os.environ.get('RIGL_STEM_S2D', '1') != '0'
 
 
 class Profiler(object):

@@ -168,19 +168,27 @@ def test_conv_stem_window_path(case):
     layers.STEM_WINDOW_PATH = False
 
 
-@pytest.mark.skipif(__import__('os').environ.get('RIGL_TEST_EXPERIMENTAL') != '1',
-                    reason='experimental space-to-depth stem kernels: not yet validated on hardware '
-                           '(run tools/umma_sw32_probe.cu first, then RIGL_TEST_EXPERIMENTAL=1)')
 @pytest.mark.parametrize('case', [(2, 16, 16, 3, 64, 7, 2, 0.14), (3, 32, 32, 3, 64, 7, 2, 0.14),
                                   (2, 64, 48, 3, 16, 7, 2, 0.5), (2, 224, 224, 3, 64, 7, 2, 0.14)])
 def test_conv_stem_s2d_path(case):
-  """The opt-in space-to-depth stem (layers.STEM_S2D_PATH): same oracle, same tolerances."""
+  """The space-to-depth stem (layers.STEM_S2D_PATH, the default): same oracle, same tolerances."""
   from rigl_b200 import layers
-  layers.STEM_S2D_PATH = True
+  old, layers.STEM_S2D_PATH = layers.STEM_S2D_PATH, True
   try:
     _conv_case(case, force_simt=False)
   finally:
-    layers.STEM_S2D_PATH = False
+    layers.STEM_S2D_PATH = old
+
+
+@pytest.mark.parametrize('case', [(3, 32, 32, 3, 64, 7, 2, 0.14), (2, 64, 48, 3, 16, 7, 2, 0.5)])
+def test_conv_stem_patch_matrix_path(case):
+  """RIGL_STEM_S2D=0 fallback: the im2col patch-matrix stem."""
+  from rigl_b200 import layers
+  old, layers.STEM_S2D_PATH = layers.STEM_S2D_PATH, False
+  try:
+    _conv_case(case, force_simt=False)
+  finally:
+    layers.STEM_S2D_PATH = old
 
 
 @pytest.mark.parametrize('case', [CONV_CASES[5], CONV_CASES[8], CONV_CASES[10], CONV_CASES[11]])

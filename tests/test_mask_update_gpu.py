@@ -274,8 +274,6 @@ def _gdec(e):
   return None if e is None else np.frombuffer(bytes.fromhex(e['hex']), dtype=np.dtype(e['dtype'])).reshape(e['shape']).copy()
 
 
-@pytest.mark.skipif(_os.environ.get('RIGL_TEST_EXPERIMENTAL') != '1',
-                    reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
 @pytest.mark.parametrize('case', _GOLD['cases'], ids=[c['tag'] for c in _GOLD['cases']])
 def test_cuda_update_on_reference_executed_golden_inputs(case):
   i = case['in']

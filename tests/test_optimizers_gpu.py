@@ -199,13 +199,8 @@ def test_rigl_update_through_public_api_matches_oracle():
     assert l.mask.count_ones() == int(s['mask'].sum())
 
 
-# ---- SparseMomentumOptimizer (sparse_optimizers.py:126-214).  The host logic is covered on the CPU
-# (tests/test_oracle_other_optimizers.py); these two run the real layers + select kernels and were
-# written after the round's GPU budget was spent, so they are gated until their first validated run.
-_EXPERIMENTAL = __import__('os').environ.get('RIGL_TEST_EXPERIMENTAL') == '1'
-
-
-@pytest.mark.skipif(not _EXPERIMENTAL, reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
+# ---- SparseMomentumOptimizer (sparse_optimizers.py:126-214).  The host logic is also covered on the CPU
+# (tests/test_oracle_other_optimizers.py); these two run the real layers + select kernels.
 @pytest.mark.parametrize('n_inp,n_out,momentum', [(3, 4, 0.5), (5, 2, 0.), (2, 5, 1.)])
 def test_momentum_update(n_inp, n_out, momentum):
   """sparse_optimizers_test.py:276-295 (testMomentumUpdate)."""
@@ -225,7 +220,6 @@ def test_momentum_update(n_inp, n_out, momentum):
     assert np.array_equal(got, current.astype(np.float32))
 
 
-@pytest.mark.skipif(not _EXPERIMENTAL, reason='not yet validated on hardware (RIGL_TEST_EXPERIMENTAL=1 to run)')
 def test_momentum_mask_update_matches_oracle():
   pruning.reset_default_registry()
   torch.manual_seed(2)
