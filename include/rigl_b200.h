@@ -78,7 +78,8 @@ RIGL_API int rigl_apply_mask_f32(const float* src, const uint32_t* bits, int64_t
  * ---------------------------------------------------------------------- */
 typedef struct {
   float* weights;            /* [n] in/out: grown entries are overwritten        */
-  const float* score_grow;   /* [n] dense dL/d(mask*w) (RigL) | U[0,1) (SET) | mask (Static) */
+  const float* score_grow;   /* [n] dense dL/d(mask*w) (RigL) | U[0,1) (SET) | mask (Static); ranked by
+                                |score_grow| unless RIGL_LAYER_GROW_SCORE_SIGNED is set in `flags` */
   uint32_t* mask_bits;       /* [rigl_mask_words(n)] in/out                      */
   const float* noise;        /* [n] added to |mask*w| before ranking, or NULL    */
   float* slots[2];           /* optimizer slots reset at new connections, or NULL */
@@ -87,8 +88,16 @@ typedef struct {
                                 the `_get_update_op(score_drop, ...)` entry, base.py:276 */
   int64_t n;                 /* elements, 1 <= n < 2^31                          */
   int32_t n_prune_override;  /* >= 0: use this n_prune; -1: int32(float32(n_ones)*drop_fraction) */
-  int32_t reserved;
+  int32_t flags;             /* RIGL_LAYER_* bits */
+  const float* grad;         /* [n] gradient read by RIGL_GROW_GRAD_SCALE / _SIGN and by the slot reset
+                                (slot <- grad * acc_scale), base.py:540-564; NULL: score_grow is the gradient
+                                (the RigL / Momentum callers, whose grow score IS the dense gradient) */
 } rigl_layer_desc;
+
+/* rigl_layer_desc.flags */
+#define RIGL_LAYER_GROW_SCORE_SIGNED 1  /* rank score_grow verbatim (signed), as `_get_update_op(score_drop,
+                                           score_grow, ...)` (base.py:276-343) does with caller-built scores,
+                                           e.g. the rigl_tf2 updaters' -|g|; default ranks |score_grow| */
 
 typedef enum {
   RIGL_GROW_ZEROS = 0,       /* 'zeros'            base.py:372-373 */

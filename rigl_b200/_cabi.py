@@ -19,7 +19,7 @@ class RiglError(RuntimeError):
 class LayerDesc(C.Structure):
   _fields_ = [('weights', C.c_void_p), ('score_grow', C.c_void_p), ('mask_bits', C.c_void_p),
               ('noise', C.c_void_p), ('slots', C.c_void_p * 2), ('grow_values', C.c_void_p), ('score_drop', C.c_void_p),
-              ('n', C.c_int64), ('n_prune_override', C.c_int32), ('reserved', C.c_int32)]
+              ('n', C.c_int64), ('n_prune_override', C.c_int32), ('flags', C.c_int32), ('grad', C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -29,6 +29,7 @@ class ConvDesc(C.Structure):
 
 
 GROW_ZEROS, GROW_TENSOR, GROW_GRAD_SCALE, GROW_GRAD_SIGN = 0, 1, 2, 3
+LAYER_GROW_SCORE_SIGNED = 1
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 

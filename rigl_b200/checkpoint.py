@@ -37,9 +37,23 @@ def _tensor_handle(t):
   return Handle(get, set_)
 
 
-def variables_of(model, optimizer=None):
+def _scalar_handle(get, set_):
+  return Handle(lambda: np.asarray(get(), dtype=np.float64), lambda a: set_(np.asarray(a).reshape(-1)[0]))
+
+
+def variables_of(model, optimizer=None, sparse_optimizer=None, ckpt_path=None):
   """OrderedDict name -> Handle for a rigl_b200 model: masks, masked weights, the remaining
-  parameters / buffers and (optionally) the inner optimizer's per-parameter state tensors."""
+  parameters / buffers, (optionally) the inner optimizer's per-parameter state tensors and the sparse
+  optimizer's own state.
+
+  sparse_optimizer: adds `last_mask_update_step` -- a non-trainable global variable in the reference
+    (sparse_optimizers_base.py:166-171), so it lives in its checkpoints; without it a resumed run would
+    re-initialise it to -frequency and fire an off-schedule mask update -- and, for
+    SparseMomentumOptimizer, the EMA shadows `<scope>/weights/ExponentialMovingAverage`.
+  ckpt_path: a checkpoint about to be restored.  A freshly built torch optimizer has an EMPTY state, so
+    its slots (`<scope>/weights/momentum_buffer` ...) would be skipped silently; every slot the file holds
+    for a known parameter is materialised (zeros) in `optimizer.state` here so that restore() fills it."""
+  import torch
   out = collections.OrderedDict()
   masked = {}
   for l in model.registry.layers():
@@ -51,10 +65,29 @@ def variables_of(model, optimizer=None):
       out[name.replace('.', '/')] = _tensor_handle(p)
   if optimizer is not None:
     names = {id(p): (masked.get(id(p)) or n.replace('.', '/')) for n, p in model.named_parameters()}
+    if ckpt_path is not None:
+      by_name = {v: p for p in (q for g in optimizer.param_groups for q in g['params'])
+                 for v in [names.get(id(p))] if v is not None}
+      with np.load(ckpt_path) as z:
+        for key in z.files:
+          base, _, slot = key.rpartition('/')
+          p = by_name.get(base)
+          if p is not None and key not in out and z[key].size == p.numel() and slot not in optimizer.state[p]:
+            optimizer.state[p][slot] = torch.zeros_like(p)
     for p, st in optimizer.state.items():
       for k, v in st.items():
         if hasattr(v, 'shape') and tuple(v.shape) == tuple(p.shape):
           out['%s/%s' % (names.get(id(p), 'param%d' % id(p)), k)] = _tensor_handle(v)
+  if sparse_optimizer is not None:
+    so = sparse_optimizer
+    out['last_mask_update_step'] = _scalar_handle(
+        so._last_update_value, lambda v: setattr(so, '_last_update_step', int(v)))
+    if hasattr(so, '_ema'):
+      for l in model.registry.layers():
+        name = l.weight.name
+        if name not in so._ema:
+          so._ema[name] = torch.zeros(l.weight.numel(), dtype=torch.float32, device=l.weight.device)
+        out[l.scope + '/weights/ExponentialMovingAverage'] = _tensor_handle(so._ema[name])
   return out
 
 
@@ -62,7 +95,8 @@ def save(model_dir, variables, global_step):
   """Writes model.ckpt-<step>.npz; returns its path."""
   os.makedirs(model_dir, exist_ok=True)
   path = os.path.join(model_dir, 'model.ckpt-%d.npz' % int(global_step))
-  arrays = {k: np.asarray(h.get(), dtype=np.float32) for k, h in variables.items()}
+  arrays = {k: (lambda a: a if a.dtype == np.float64 else a.astype(np.float32))(np.asarray(h.get()))
+            for k, h in variables.items()}
   arrays['global_step'] = np.asarray(int(global_step), dtype=np.int64)
   tmp = path + '.tmp.npz'
   np.savez(tmp, **arrays)
@@ -86,6 +120,14 @@ def restore(path, variables, strict=True):
   """Full restore; returns the stored global step.  strict: every variable must be present with
   the right number of elements."""
   with np.load(path) as z:
+    if strict:
+      # optimizer slots / EMA shadows the file holds for a known variable but the caller has no handle for
+      # (a freshly built optimizer's state is empty): refuse to drop them silently
+      orphans = [k for k in z.files if k not in variables and k.rpartition('/')[0] in variables
+                 and k.rpartition('/')[0].endswith('weights')]
+      if orphans:
+        raise KeyError('checkpoint %s holds %d optimizer-slot variables with no handle (e.g. %s): build the '
+                       'variables with variables_of(..., ckpt_path=path)' % (path, len(orphans), orphans[0]))
     for k, h in variables.items():
       if k not in z.files:
         if strict:

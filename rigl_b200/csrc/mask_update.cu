@@ -60,6 +60,8 @@ struct LayerDev {
   float* slot1;
   const float* grow;
   const float* sdrop;
+  const float* grad;      // gradient for grad_scale / grad_sign init and the slot reset (null: score_grow is it)
+  uint32_t flags;         // RIGL_LAYER_* bits
   uint32_t n;
   int32_t n_prune_override;
   uint64_t off_mask1;   // byte offsets into the workspace
@@ -94,6 +96,12 @@ __device__ __forceinline__ float4 load4_guard(const float* __restrict__ p, uint3
     if (e0 + 2 < n) v.z = __ldg(p + e0 + 2);
   }
   return v;
+}
+
+// grow ranking key: |score| for the RigL / Momentum callers (the score IS the dense gradient and the reference
+// ranks abs(grad), base.py:529), the score verbatim for `_get_update_op(score_drop, score_grow, ...)`
+__device__ __forceinline__ uint32_t grow_key(float g, bool is_signed) {
+  return ord_key(is_signed ? g : fabsf(g));
 }
 
 __device__ __forceinline__ float drop_score(float w, uint32_t bit, float noise, bool has_noise,
@@ -304,6 +312,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const bool has_noise = L.noise != nullptr && !explicit_score;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
+  const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
   uint32_t zero_cnt = 0;
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;
@@ -357,7 +366,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
           }
         }
         if (valid && !kept && !is_cand) {          // definitely dropped / inactive: a grow contender
-          const uint32_t gkey = ord_key(fabsf(gs4[c]));
+          const uint32_t gkey = grow_key(gs4[c], grow_signed);
           if (gkey == kKeyZero) ++zero_cnt;
           else atomicAdd(&hist[gkey >> kBinShift], 1u);
         }
@@ -378,6 +387,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void apply_new_connection(const LayerDev& L, const RunParams& prm, uint32_t e,
                                                      float g) {
+  if (L.grad) g = __ldg(L.grad + e);
   float v = 0.0f;
   switch (prm.grow_mode) {
     case RIGL_GROW_TENSOR: v = __ldg(L.grow + e); break;
@@ -502,7 +512,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
         if (!was_on || prm.reinit_when_same) apply_new_connection(L, prm, e, __ldg(L.g + e));
       }
     } else if (!kGrow) {
-      const uint32_t gkey = ord_key(fabsf(__ldg(L.g + e)));
+      const uint32_t gkey = grow_key(__ldg(L.g + e), (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0);
       atomicAdd(&ghist[gkey >> kBinShift], 1u);
     }
   }
@@ -544,6 +554,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const uint32_t bucket = (uint32_t)st->grow_bucket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n = L.n;
+  const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;
 #pragma unroll 1
@@ -576,7 +587,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
         const bool contender = (e0 + c < n) && !((nib_m1 >> c) & 1u);
         uint32_t key = 0, bin = 0;
         if (contender) {
-          key = ord_key(fabsf(gs4[c]));
+          key = grow_key(gs4[c], grow_signed);
           bin = key >> kBinShift;
         }
         const bool is_cand = contender && bin == bucket;
@@ -645,11 +656,12 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
     RIGL_REQUIRE(d.n >= 1 && d.n < (1ll << 31), "layer %d: n=%lld out of range", l, (long long)d.n);
     RIGL_REQUIRE(d.weights && d.score_grow && d.mask_bits, "layer %d: null tensor", l);
     RIGL_REQUIRE(aligned16(d.weights) && aligned16(d.score_grow) && aligned16(d.mask_bits) &&
-                     aligned16(d.noise) && aligned16(d.score_drop),
+                     aligned16(d.noise) && aligned16(d.score_drop) && aligned16(d.grad),
                  "layer %d: weights/score_grow/mask_bits/noise/score_drop must be 16-byte aligned", l);
     LayerDev& L = host[l];
     L.w = d.weights; L.g = d.score_grow; L.mask = d.mask_bits; L.noise = d.noise;
     L.slot0 = d.slots[0]; L.slot1 = d.slots[1]; L.grow = d.grow_values; L.sdrop = d.score_drop;
+    L.grad = d.grad; L.flags = (uint32_t)d.flags;
     L.n = (uint32_t)d.n; L.n_prune_override = d.n_prune_override;
     L.off_state = state_off + sizeof(LayerState) * (size_t)l;
     L.off_hist_drop = hist_drop_off + (size_t)l * kBins * 4;

@@ -206,9 +206,11 @@ class _MaskedConvFn(torch.autograd.Function):
         _WS_SLOT[0] = 'main'
       _SIDE_KEEP.append((x, dy16, patch_keep))     # no reuse of these blocks before the join
       mw.fresh = True
+      mw.dense_grad.rigl_reduced = False           # rewritten: not yet summed over the replicas
     else:
       _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
       mw.fresh = True
+      mw.dense_grad.rigl_reduced = False
       if ctx.needs_input_grad[1]:
         gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
     gb = None

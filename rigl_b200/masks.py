@@ -90,7 +90,9 @@ class MaskUpdateEngine(object):
 
   Each layer is a dict with tensors (float32, contiguous, same numel):
     weights, score_grow, mask (MaskVariable), and optional noise, slots (list of
-    up to 2 tensors), grow_values, score_drop, n_prune (int override).
+    up to 2 tensors), grow_values, score_drop, n_prune (int override), grad (the gradient the
+    grad_* grow inits and the slot reset read when it is not score_grow itself) and flags
+    (_cabi.LAYER_GROW_SCORE_SIGNED: rank score_grow verbatim instead of |score_grow|).
   The C plan captures raw pointers, so it is rebuilt whenever any pointer changes.
   """
 
@@ -116,7 +118,8 @@ class MaskUpdateEngine(object):
     slots = list(ly.get('slots') or [])
     return (ly['weights'].data_ptr(), ly['score_grow'].data_ptr(), ly['mask'].bits.data_ptr(),
             _ptr(ly.get('noise')), tuple(s.data_ptr() for s in slots), _ptr(ly.get('grow_values')),
-            _ptr(ly.get('score_drop')), int(ly['mask'].size), int(ly.get('n_prune', -1)))
+            _ptr(ly.get('score_drop')), int(ly['mask'].size), int(ly.get('n_prune', -1)),
+            _ptr(ly.get('grad')), int(ly.get('flags', 0)))
 
   def prepare(self, layers):
     key = tuple(self._layer_key(ly) for ly in layers)
@@ -126,7 +129,7 @@ class MaskUpdateEngine(object):
     descs = (_cabi.LayerDesc * len(layers))()
     for d, ly in zip(descs, layers):
       n = ly['mask'].size
-      for name in ('weights', 'score_grow', 'noise', 'grow_values', 'score_drop'):
+      for name in ('weights', 'score_grow', 'noise', 'grow_values', 'score_drop', 'grad'):
         t = ly.get(name)
         if t is not None:
           if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or not t.is_cuda:
@@ -145,6 +148,8 @@ class MaskUpdateEngine(object):
         d.slots[i] = s.data_ptr()
       d.grow_values = _ptr(ly.get('grow_values'))
       d.score_drop = _ptr(ly.get('score_drop'))
+      d.grad = _ptr(ly.get('grad'))
+      d.flags = int(ly.get('flags', 0))
       d.n = n
       d.n_prune_override = int(ly.get('n_prune', -1))
     plan = C.c_void_p(None)

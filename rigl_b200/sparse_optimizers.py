@@ -1,9 +1,9 @@
 """Concrete sparse optimizers bound to the PyTorch masked-layer registry.
 
 Mirror of rigl/sparse_optimizers.py:46-123 (PruningGetterTf1Mixin,
-SparseSETOptimizer, SparseRigLOptimizer, SparseStaticOptimizer).  The momentum /
-SNIP / DNW optimizers of the reference (:126-480) reuse the same select
-primitive and are listed as "next" in DESIGN.md.
+SparseSETOptimizer, SparseRigLOptimizer, SparseStaticOptimizer) and of the
+momentum / SNIP / DNW optimizers (:126-480), which reuse the same batched
+select kernels with different scores.
 """
 from . import pruning
 from . import sparse_optimizers_base as sparse_opt_base
@@ -60,10 +60,10 @@ class SparseStaticOptimizer(SparseSETOptimizer):
     return mask.to_dense().view(-1)
 
   def _layer_spec(self, mask, weights, noise_std, score_drop=None, score_grow=None,
-                  reinit_when_same=True, noise=None):
+                  reinit_when_same=True, noise=None, signed_grow=False):
     return super(SparseStaticOptimizer, self)._layer_spec(
         mask, weights, noise_std, score_drop=score_drop, score_grow=score_grow,
-        reinit_when_same=True, noise=noise)
+        reinit_when_same=True, noise=noise, signed_grow=signed_grow)
 
 
 class SparseMomentumOptimizer(SparseSETOptimizer):
@@ -89,12 +89,7 @@ class SparseMomentumOptimizer(SparseSETOptimizer):
 
   def set_masked_grads(self, grads, weights):
     """reference :176-181 (cross-replica SUM of the dense grads when `use_tpu`)."""
-    import torch
-    if self._use_tpu and torch.distributed.is_available() and torch.distributed.is_initialized() \
-        and torch.distributed.get_world_size() > 1:
-      for g in grads:
-        if not getattr(g, 'rigl_reduced', False):
-          torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
+    sparse_opt_base.cross_replica_sum_(grads, self._use_tpu)
     self._masked_grads = list(grads)
     self._weight2masked_grads = {w.name: g for w, g in zip(weights, grads)}
 
@@ -110,8 +105,7 @@ class SparseMomentumOptimizer(SparseSETOptimizer):
   def _before_apply_gradients(self, grads_and_vars):
     """Updates the EMA before the weights move (reference :195-197)."""
     import torch
-    if not self._masked_grads:
-      self.collect_masked_grads()
+    self.collect_masked_grads()          # every step: the buffers may have been rebound / rewritten
     c = 1.0 - self._momentum
     for w, g in zip(self.get_weights(), self._masked_grads):
       ema = self._ema.get(w.name)

@@ -98,6 +98,19 @@ def host_drop_fraction(anneal, initial_value, global_step, begin_step, end_step)
   raise ValueError('drop_fraction_anneal: %s is not valid' % anneal)
 
 
+def cross_replica_sum_(grads, enabled):
+  """tpu_ops.cross_replica_sum of base.py:471-476: SUM every dense-gradient buffer over the replicas, once
+  per backward -- a buffer carries `rigl_reduced` from the moment it is summed until the masked layer's
+  next backward rewrites it (layers._MaskedConvFn.backward clears the flag)."""
+  if not (enabled and torch.distributed.is_available() and torch.distributed.is_initialized()
+          and torch.distributed.get_world_size() > 1):
+    return
+  for g in grads:
+    if not getattr(g, 'rigl_reduced', False):
+      torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
+      g.rigl_reduced = True
+
+
 class SparseSETOptimizerBase(object):
   """Wraps a torch optimizer; periodically drops by magnitude and regrows at random."""
 
@@ -211,7 +224,12 @@ class SparseSETOptimizerBase(object):
     self._inner_step(grads_and_vars, global_step)
     gs = global_step if global_step is not None else get_or_create_global_step()
     self._global_step = gs
-    return self.cond_mask_update_op(gs, lambda: None)
+    try:
+      return self.cond_mask_update_op(gs, lambda: None)
+    finally:
+      # the gradients of this step are consumed: the next backward OVERWRITES the dense-grad buffers
+      # whichever zero_grad() the caller uses (the reference recomputes them every step)
+      self._mark_dense_grads_stale()
 
   def minimize(self, loss, global_step=None, **kwargs):
     return self.apply_gradients(self.compute_gradients(loss, **kwargs), global_step=global_step)
@@ -322,8 +340,12 @@ class SparseSETOptimizerBase(object):
   def _acc_scale(self):
     return 0.0
 
+  def _grad_for(self, weights):
+    """The gradient the grad_* grow inits / slot reset read when the grow score is NOT it (explicit scores)."""
+    return None
+
   def _layer_spec(self, mask, weights, noise_std, score_drop=None, score_grow=None,
-                  reinit_when_same=False, noise=None):
+                  reinit_when_same=False, noise=None, signed_grow=False):
     mode, div, grow_values = self._grow_spec(weights, self._grow_init)
     if score_grow is None:
       score_grow = self._score_grow_for(mask, weights)
@@ -333,7 +355,9 @@ class SparseSETOptimizerBase(object):
                 noise=None if score_drop is not None else noise,
                 score_drop=None if score_drop is None else score_drop.contiguous().view(-1),
                 slots=self._slots_of(weights), grow_values=grow_values, grow_mode=mode,
-                grow_divisor=div, reinit_when_same=reinit_when_same)
+                grow_divisor=div, reinit_when_same=reinit_when_same,
+                flags=_cabi.LAYER_GROW_SCORE_SIGNED if signed_grow else 0,
+                grad=self._grad_for(weights) if signed_grow else None)
 
   def _run_update(self, specs):
     modes = {(s['grow_mode'], s['grow_divisor'], s['reinit_when_same']) for s in specs}
@@ -349,10 +373,12 @@ class SparseSETOptimizerBase(object):
     return mask
 
   def _get_update_op(self, score_drop, score_grow, mask, weights, reinit_when_same=False):
-    """Prune + grow one layer from explicit score tensors (all of `mask.shape`)."""
+    """Prune + grow one layer from explicit score tensors (all of `mask.shape`), both used VERBATIM
+    (signed) like base.py:276-343: top-k of score_drop keeps, top-k of score_grow among the rest grows.
+    The grad_* grow inits and the RigL slot reset read the stored dense gradient, not score_grow."""
     self._run_update([self._layer_spec(mask, weights, 0., score_drop=score_drop.float(),
                                        score_grow=score_grow.float(),
-                                       reinit_when_same=reinit_when_same)])
+                                       reinit_when_same=reinit_when_same, signed_grow=True)])
     return mask
 
   def reset_momentum(self, weights, new_connections):
@@ -431,11 +457,7 @@ class SparseRigLOptimizerBase(SparseSETOptimizerBase):
 
   def set_masked_grads(self, grads, weights):
     """Stores dL/d(mask*w) per weight name; cross-replica SUM when `use_tpu`."""
-    if self._use_tpu and torch.distributed.is_available() and torch.distributed.is_initialized() \
-        and torch.distributed.get_world_size() > 1:
-      for g in grads:
-        if not getattr(g, 'rigl_reduced', False):
-          torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
+    cross_replica_sum_(grads, self._use_tpu)
     self._masked_grads = list(grads)
     self._weight2masked_grads = {w.name: g for w, g in zip(weights, grads)}
 
@@ -454,12 +476,21 @@ class SparseRigLOptimizerBase(SparseSETOptimizerBase):
     self._before_apply_gradients(grads_and_vars)
     gs = global_step if global_step is not None else get_or_create_global_step()
     self._global_step = gs
-    if not self._weight2masked_grads:
-      self.collect_masked_grads()
-    return self.cond_mask_update_op(gs, lambda: self._inner_step(grads_and_vars, global_step))
+    # every step (the reference's compute_gradients runs cross_replica_sum every step, base.py:471-485);
+    # buffers a DataParallel wrapper or compute_gradients already reduced carry `rigl_reduced` and are
+    # not summed twice
+    self.collect_masked_grads()
+    try:
+      return self.cond_mask_update_op(gs, lambda: self._inner_step(grads_and_vars, global_step))
+    finally:
+      self._mark_dense_grads_stale()
 
   def _score_grow_for(self, mask, weights):
     return self._weight2masked_grads[weights.name]       # |.| is taken in the kernel
+
+  def _grad_for(self, weights):
+    g = self._weight2masked_grads.get(weights.name)
+    return None if g is None else g.contiguous().view(-1)
 
   def _acc_scale(self):
     return self._initial_acc_scale

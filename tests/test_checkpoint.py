@@ -110,3 +110,26 @@ def test_variables_of_names_follow_reference_scopes(tmp_path):
   net.l1.mask.assign(np.zeros((4, 3)))
   assert ck.restore(path, ck.variables_of(net, opt)) == 7
   assert torch.equal(net.l1.weight.detach(), w) and net.l1.mask.numpy().sum() == 12
+
+
+def test_strict_restore_refuses_to_drop_optimizer_slots(tmp_path):
+  """A checkpoint with `<scope>/weights/<slot>` entries restored into variables without those handles
+  (fresh optimizer, empty state) must fail loudly rather than skip the momentum buffers."""
+  src, svars = _vars(5)
+  path = ck.save(str(tmp_path / 'run'), svars, 7)
+  dst, dvars = _vars(6)
+  del dvars['net/layer1/weights/momentum_buffer']
+  with pytest.raises(KeyError):
+    ck.restore(path, dvars)
+  ck.restore(path, dvars, strict=False)
+
+
+def test_scalar_state_roundtrip(tmp_path):
+  """last_mask_update_step travels as a float64 scalar (sparse_optimizers_base.py:166-171)."""
+  state = {'v': -100}
+  variables = {'last_mask_update_step': ck._scalar_handle(lambda: state['v'], lambda v: state.update(v=int(v)))}
+  state['v'] = 1300
+  path = ck.save(str(tmp_path / 'r'), variables, 1342)
+  state['v'] = -100
+  assert ck.restore(path, variables) == 1342
+  assert state['v'] == 1300

@@ -290,3 +290,40 @@ def test_cuda_update_on_reference_executed_golden_inputs(case):
   _run_case([layer], np.float32(float.fromhex(case['drop_fraction'])), grow_mode=mode, grow_divisor=div,
             acc_scale=float(np.float32(float.fromhex(case['initial_acc_scale']))), reinit=case['reinit_when_same'],
             check_stats=False)
+
+
+@pytest.mark.parametrize('mode', ['zeros', 'grad_scale', 'grad_sign'])
+def test_explicit_signed_grow_scores_with_separate_gradient(mode):
+  """`_get_update_op(score_drop, score_grow, ...)` ranks score_grow VERBATIM (base.py:305-318): the rigl_tf2
+  updaters pass -|g|, i.e. all-negative scores whose order is the reverse of |g|'s.  The grad_* grow inits and
+  the slot reset then read the stored dense gradient (base.py:540-564), not the score."""
+  rng = np.random.RandomState(11)
+  shape = (96, 130)
+  m = orc.get_mask_random_numpy(shape, 0.7, rng).astype(np.float32)
+  w = rng.standard_normal(shape).astype(np.float32)
+  grad = rng.standard_normal(shape).astype(np.float32)
+  sg = (-np.abs(grad) * (1 + rng.randint(0, 3, shape))).astype(np.float32)      # negative, ties, not |grad| order
+  sg[rng.rand(*shape) < 0.05] = -0.0
+  sd = (np.abs(w) * m + rng.standard_normal(shape) * 0.1).astype(np.float32)   # signed drop scores too
+  slot = rng.standard_normal(shape).astype(np.float32)
+  gmode, div, grow = _cabi.GROW_ZEROS, 1.0, None
+  if mode == 'grad_scale':
+    gmode, div, grow = _cabi.GROW_GRAD_SCALE, 4.0, (grad / np.float32(4.0)).astype(np.float32)
+  elif mode == 'grad_sign':
+    gmode, div, grow = _cabi.GROW_GRAD_SIGN, 8.0, (np.sign(grad) / np.float32(8.0)).astype(np.float32)
+  acc = 0.25
+  want = orc.get_update_op(sd, sg, m, w, np.float32(0.4), grow_tensor=grow, slots=[slot],
+                           slot_reset=(grad * np.float32(acc)).astype(np.float32))
+  mv = MaskVariable('signed', shape, DEV).assign(m)
+  wd, sl = _t(w).view(-1), _t(slot).view(-1)
+  spec = dict(mask=mv, weights=wd, score_grow=_t(sg).view(-1), score_drop=_t(sd).view(-1), slots=[sl],
+              grad=_t(grad).view(-1), flags=_cabi.LAYER_GROW_SCORE_SIGNED)
+  MaskUpdateEngine().run([spec], np.float32(0.4), grow_mode=gmode, grow_divisor=div, acc_scale=acc)
+  assert np.array_equal(mv.numpy(), want['mask'])
+  assert wd.cpu().numpy().reshape(shape).tobytes() == want['weights'].tobytes()
+  assert sl.cpu().numpy().reshape(shape).tobytes() == want['slots'][0].tobytes()
+  # and the default (|score|) ranking really differs on this input
+  mv2 = MaskVariable('abs', shape, DEV).assign(m)
+  MaskUpdateEngine().run([dict(mask=mv2, weights=_t(w).view(-1), score_grow=_t(sg).view(-1),
+                               score_drop=_t(sd).view(-1))], np.float32(0.4))
+  assert not np.array_equal(mv2.numpy(), want['mask'])

@@ -244,3 +244,47 @@ def test_momentum_mask_update_matches_oracle():
   ema_after = orc.momentum_ema_update(ema_before, g, 0.9)
   assert np.array_equal(so.ema_average(layer.weight).cpu().numpy(), ema_after)
   assert layer.mask.count_ones() == int(mask0.sum())
+
+
+@pytest.mark.parametrize('clear', ['inner_zero_grad', 'module_zero_grad', 'set_to_none', 'never'])
+def test_dense_grads_do_not_accumulate_across_steps_whichever_zero_grad(clear):
+  """torch-style loop `backward(); opt.step()` where the caller clears gradients on the INNER optimizer /
+  the module (or not at all): the dense gradient RigL ranks must be this step's gradient, like the
+  reference's per-step compute_gradients (base.py:478-485), not a running sum."""
+  pruning.reset_default_registry()
+  layer = SparseLinear(6, 5, name='fully_connected', device=DEV, out_dtype=torch.float32)
+  inner = torch.optim.SGD(layer.parameters(), lr=0.0)
+  so = sparse_optimizers.SparseRigLOptimizer(inner, 100, 200, 50, drop_fraction=0.3)      # no update in range
+  gs = GlobalStep(0)
+  x = torch.ones(1, 6, device=DEV)
+  coeff = torch.arange(5, device=DEV, dtype=torch.float32)
+  for step in range(4):
+    if clear == 'inner_zero_grad':
+      inner.zero_grad()
+    elif clear == 'module_zero_grad':
+      layer.zero_grad()
+    elif clear == 'set_to_none':
+      inner.zero_grad(set_to_none=True)
+    (layer(x) * coeff).sum().backward()
+    g = layer.masked_weights.dense_grad.view(6, 5).cpu().numpy()
+    assert np.array_equal(g, np.tile(np.arange(5, dtype=np.float32), (6, 1))), (clear, step)
+    so.step(gs)
+  assert gs.value == 4
+
+
+def test_get_update_op_uses_scores_verbatim():
+  """Public `_get_update_op` with NEGATIVE grow scores (the rigl_tf2 updaters pass -|g|): ranked as given."""
+  pruning.reset_default_registry()
+  rng = np.random.RandomState(3)
+  layer = SparseLinear(40, 30, name='fully_connected', device=DEV, out_dtype=torch.float32)
+  m = orc.get_mask_random_numpy((40, 30), 0.6, rng).astype(np.float32)
+  layer.mask.assign(m)
+  w = layer.weight.detach().cpu().numpy().copy()
+  so = sparse_optimizers.SparseSETOptimizer(torch.optim.SGD(layer.parameters(), lr=0.1), 0, 10, 1, drop_fraction=0.5)
+  so.drop_fraction = np.float32(0.5)
+  sd = (np.abs(w) * m).astype(np.float32)
+  sg = (-rng.rand(40, 30)).astype(np.float32)
+  so._get_update_op(torch.from_numpy(sd).to(DEV), torch.from_numpy(sg).to(DEV), layer.mask, layer.weight)
+  want = orc.get_update_op(sd, sg, m, w, np.float32(0.5))
+  assert np.array_equal(layer.mask.numpy(), want['mask'])
+  assert layer.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes()
