@@ -92,7 +92,7 @@ def test_momentum_optimizer_host_logic_matches_oracle(n_inp, n_out, momentum):
   opt = SparseMomentumOptimizer(torch.optim.SGD([w], lr=0.1), 1, 4, 2, drop_fraction=0.5, momentum=momentum)
   g = torch.arange(n_out, dtype=torch.float32).repeat(n_inp, 1).contiguous().view(-1)
   opt.get_weights = lambda: [W]
-  opt.get_masked_weights = lambda: []
+  opt.get_masked_weights = lambda: [__import__('types').SimpleNamespace(dense_grad=g, fresh=True)]
   opt.set_masked_grads([g], [W])
   ema = np.zeros(n_inp * n_out, np.float32)
   for _ in range(6):
