@@ -1,14 +1,17 @@
-"""Benchmark of the RigL hot path: sparse ResNet-50 train step + mask update.
+"""Benchmark of the RigL hot path: sparse train step (+ the periodic mask update) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Metric (BASELINE.json): sparse train-step images/sec, ResNet-50, 80 % ERK, bf16,
-batch 256 per GPU (configs[1]; weak scaling: 256 images per GPU at every N),
-synthetic ImageNet-shaped data, RigL schedule drop 0.3 / cosine / every 100
-steps, so a 100-step timed region contains exactly one mask update.
-One JSON line on rank 0; keys per the driver contract plus `roofline`,
-`cpu_baseline`, `mask_update_ms`.
+Configs (BASELINE.json `configs`; the metric is quoted on c2, the default):
+  c2  ResNet-50, ImageNet-shaped synthetic, 80 % ERK, bf16, batch 256 per GPU
+  c3  ResNet-50, 90 % ERK, batch 256 per GPU (global 2048 at 8 GPUs)
+  c4  MobileNet-v1, 90 % uniform on the 13 pointwise convs + classifier (~89 % overall), batch 256 per GPU
+  c5  WideResNet-22-2, CIFAR-shaped synthetic, 95 % ERK, batch 128 per GPU, mask update every 100 steps
+All: RigL, drop fraction 0.3 cosine, update every 100 steps, Nesterov momentum, weak scaling (fixed per-GPU
+batch).  The timed region always contains ceil(steps/100) mask updates (the schedule is aligned so that the
+first one falls in the middle of the region), so `value` includes their cost at the reference's own cadence
+or denser.  One JSON line on rank 0: the driver contract plus `roofline`, `cpu_baseline`, `mask_update_ms`.
 """
 import argparse
 import json
@@ -24,15 +27,22 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 256
-IMAGE = 224
-SPARSITY = 0.8
-METRIC = 'sparse_train_step_images_per_sec_resnet50_erk80'
-# masked FLOPs per image, 2*MAC, maskable layers only.  This build computes the
-# DENSE wgrad every step (as the TF reference effectively does), so the "update step"
-# accounting 2*f_S + f_D - f_S(first conv) applies to every step.
-ALG_GFLOP_PER_IMAGE = 14.744
-DENSE_GFLOP_PER_IMAGE = 3 * 8.178 - 0.236       # dense-executed fprop+dgrad+wgrad, no stem dgrad
+CONFIGS = {
+    'c2': dict(model='resnet50', sparsity=0.8, method='erdos_renyi_kernel', batch=256, image=224, classes=1000,
+               metric='sparse_train_step_images_per_sec_resnet50_erk80',
+               workload='ResNet-50 ImageNet-shaped, 80% ERK (54 masked tensors, 25.5M weights), batch 256/GPU'),
+    'c3': dict(model='resnet50', sparsity=0.9, method='erdos_renyi_kernel', batch=256, image=224, classes=1000,
+               metric='sparse_train_step_images_per_sec_resnet50_erk90',
+               workload='ResNet-50 ImageNet-shaped, 90% ERK (54 masked tensors, 25.5M weights), batch 256/GPU'),
+    'c4': dict(model='mobilenet_v1', sparsity=0.9, method='random', batch=256, image=224, classes=1000,
+               metric='sparse_train_step_images_per_sec_mobilenetv1_uniform90',
+               workload='MobileNet-v1 ImageNet-shaped, 90% uniform on 13 pointwise convs + classifier '
+                        '(~89% overall), depthwise convs dense (cuDNN), batch 256/GPU'),
+    'c5': dict(model='wrn22_2', sparsity=0.95, method='erdos_renyi_kernel', batch=128, image=32, classes=10,
+               metric='sparse_train_step_images_per_sec_wrn22_2_erk95',
+               workload='WideResNet-22-2 CIFAR-shaped, 95% ERK (22 masked tensors), batch 128/GPU'),
+}
+UPDATE_EVERY = 100
 
 
 def _peaks():
@@ -44,17 +54,23 @@ def _peaks():
   return 6650.0, 1400.0, 'fallback'
 
 
-def _recorded_traffic():
-  """DRAM bytes per step of the conv kernel family from the committed ncu pass
-  (profiles/r01_dram_traffic_step.json: dram__bytes_read.sum + dram__bytes_write.sum, b256)."""
-  path = os.path.join(ROOT, 'profiles', 'r01_dram_traffic_step.json')
-  try:
-    with open(path) as f:
-      d = json.load(f)
-    return {'dram_bytes_per_step': d['conv_family_dram_bytes_per_step'], 'launches': d['conv_family_launches'],
-            'source': 'profiles/r01_dram_traffic_step.json'}
-  except Exception:
+def _recorded_traffic(cfg_name):
+  """DRAM bytes per step of the conv kernel family from the committed ncu pass of the SAME workload
+  (profiles/*_dram_traffic_step.json: dram__bytes_read.sum + dram__bytes_write.sum, c2 at batch 256).  ncu
+  cannot run inside a timed bench, so this is the recorded capture, not a live measurement; null for the
+  configs that have no capture."""
+  if cfg_name != 'c2':
     return None
+  for name in ('r02_dram_traffic_step.json', 'r01_dram_traffic_step.json'):
+    path = os.path.join(ROOT, 'profiles', name)
+    try:
+      with open(path) as f:
+        d = json.load(f)
+      return {'dram_bytes_per_step': d['conv_family_dram_bytes_per_step'], 'launches': d['conv_family_launches'],
+              'source': 'profiles/' + name + ' (recorded ncu capture, not measured by this run)'}
+    except Exception:
+      continue
+  return None
 
 
 class ClockSampler(object):
@@ -108,25 +124,75 @@ def _dist_setup(n_gpus):
   return None, 0, 1, 0
 
 
+def build_model(cfg, dev):
+  from rigl_b200 import workloads
+  if cfg['model'] == 'resnet50':
+    model = workloads.ResNet50(num_classes=cfg['classes'], device=dev)
+  elif cfg['model'] == 'mobilenet_v1':
+    model = workloads.MobileNetV1(num_classes=cfg['classes'], device=dev)
+  else:
+    model = workloads.WideResNet(depth=22, width=2, num_classes=cfg['classes'], device=dev)
+  workloads.init_masks(model, cfg['method'], cfg['sparsity'], seed=0)
+  return model
+
+
+def masked_flops_per_image(model, image, dev):
+  """SURVEY 8(d) accounting from the model's own masked layers: per image, 2*MAC, maskable layers only.
+  f_D = dense-executed fprop FLOPs, f_S = the same scaled by each layer's density.  This build computes the DENSE
+  wgrad every step (as the TF1 reference effectively does), so a step costs
+    algorithmic = 2*f_S + f_D - f_S(first masked conv: no input gradient);  dense-executed = 3*f_D - f_D(first)."""
+  from rigl_b200.layers import SparseConv2d
+  shapes = {}
+  hooks = []
+  for l in model.registry.layers():
+    hooks.append(l.register_forward_hook(lambda mod, inp, out, l=l: shapes.__setitem__(l.scope, tuple(out.shape))))
+  was = model.training
+  model.eval()
+  with torch.no_grad():
+    model(torch.zeros(1, 3, image, image, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+  model.train(was)
+  for h in hooks:
+    h.remove()
+  f_d = f_s = 0.0
+  first_d = first_s = None
+  for l in model.registry.layers():
+    sh = shapes[l.scope]
+    pixels = sh[2] * sh[3] if len(sh) == 4 else 1
+    macs = pixels * l.weight.numel()
+    dens = l.mask.count_ones() / float(l.mask.size)
+    f_d += 2.0 * macs
+    f_s += 2.0 * macs * dens
+    if first_d is None and isinstance(l, SparseConv2d) and l.in_channels == 3:
+      first_d, first_s = 2.0 * macs, 2.0 * macs * dens
+  first_d, first_s = first_d or 0.0, first_s or 0.0
+  return {'f_dense_gflop': f_d / 1e9, 'f_sparse_gflop': f_s / 1e9,
+          'algorithmic_gflop': (2 * f_s + f_d - first_s) / 1e9, 'dense_executed_gflop': (3 * f_d - first_d) / 1e9}
+
+
 def run_ours(args):
   from rigl_b200 import _cabi
   from rigl_b200 import workloads
   from rigl_b200.layers import Profiler
 
+  cfg = CONFIGS[args.config]
+  batch, image = cfg['batch'], cfg['image']
   dist, rank, world, local = _dist_setup(args.gpus)
   dev = torch.device('cuda', local)
   torch.manual_seed(0)
-  model = workloads.ResNet50(device=dev)
-  workloads.init_masks(model, 'erdos_renyi_kernel', SPARSITY, seed=0)
+  model = build_model(cfg, dev)
+  flops = masked_flops_per_image(model, image, dev)
   dp = None
   if world > 1:
     from rigl_b200.data_parallel import DataParallel
     dp = DataParallel()
-  harness = workloads.TrainHarness(model, lr=0.1, data_parallel=dp)
+  wd = 5e-4 if cfg['model'] == 'wrn22_2' else 1e-4
+  smooth = 0.0 if cfg['model'] == 'wrn22_2' else 0.1
+  harness = workloads.TrainHarness(model, lr=0.1, weight_decay=wd, label_smoothing=smooth, frequency=UPDATE_EVERY,
+                                   data_parallel=dp)
   g = torch.Generator(device=dev).manual_seed(1 + rank)
-  images = torch.randn(BATCH, 3, IMAGE, IMAGE, device=dev, generator=g).to(torch.bfloat16) \
+  images = torch.randn(batch, 3, image, image, device=dev, generator=g).to(torch.bfloat16) \
       .contiguous(memory_format=torch.channels_last)
-  labels = torch.randint(0, 1000, (BATCH,), device=dev, generator=g)
+  labels = torch.randint(0, cfg['classes'], (batch,), device=dev, generator=g)
 
   def barrier():
     if dist is not None:
@@ -140,6 +206,8 @@ def run_ours(args):
     graphed = harness.enable_cuda_graph(images, labels)
   for _ in range(args.warmup):
     harness.step(images, labels)
+  # align the schedule: the next update is due in the middle of the timed region (then every 100 steps)
+  harness.opt._last_update_step = harness.global_step.value + min(args.steps, UPDATE_EVERY) // 2 - UPDATE_EVERY
   barrier()
   sampler = ClockSampler(local)
   if rank == 0:
@@ -159,11 +227,16 @@ def run_ours(args):
   if dist is not None:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
   total_ms = float(ms.item())
-  value = world * BATCH * args.steps / (total_ms / 1e3)
+  value = world * batch * args.steps / (total_ms / 1e3)
+  masks_identical = None
+  if dp is not None:
+    masks_identical = bool(dp.masks_identical(model))     # replicas must still agree after the updates
+    if not masks_identical:
+      raise RuntimeError('masks diverged across replicas')
 
   # ---- end-to-end leg: host (pinned) -> device copy of every batch, loss read back ----
   e2e_steps = max(3, min(args.steps, 20))
-  host_images = torch.empty((BATCH, IMAGE, IMAGE, 3), dtype=torch.bfloat16).pin_memory()
+  host_images = torch.empty((batch, image, image, 3), dtype=torch.bfloat16).pin_memory()
   host_images.copy_(images.permute(0, 2, 3, 1).cpu())
   host_labels = labels.cpu().pin_memory()
   barrier()
@@ -193,7 +266,7 @@ def run_ours(args):
   e_ms = torch.tensor([e_start.elapsed_time(e_stop)], device=dev, dtype=torch.float64)
   if dist is not None:
     dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-  e2e_value = world * BATCH * e2e_steps / (float(e_ms.item()) / 1e3)
+  e2e_value = world * batch * e2e_steps / (float(e_ms.item()) / 1e3)
 
   # ---- roofline leg: per-call CUDA-event times of the conv kernels (all ranks step: the
   # data-parallel all-reduce is collective; only rank 0 records) ----
@@ -224,8 +297,11 @@ def run_ours(args):
   conv_ms = sum(per_kind.get(k, 0.0) for k in ('fprop', 'dgrad', 'wgrad'))
   n_conv_launch = sum(1 for k, _, _ in rec if k in ('fprop', 'dgrad', 'wgrad')) / prof_steps
   hbm_peak, tf_peak, peak_src = _peaks()
-  achieved_tf = ALG_GFLOP_PER_IMAGE * BATCH / conv_ms            # GFLOP/ms == TFLOP/s
-  # ---- mask update alone (all 54 layers, one update) ----
+  alg = flops['algorithmic_gflop']
+  achieved_tf = alg * batch / conv_ms                             # GFLOP/ms == TFLOP/s
+  step_ms = total_ms / args.steps
+  step_tf = alg * batch * world / step_ms                         # whole job, all ranks
+  # ---- mask update alone (all masked layers, one update), through the public optimizer call ----
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   mu = []
   harness.opt.drop_fraction = np.float32(0.3)
@@ -242,14 +318,14 @@ def run_ours(args):
   total_w = sum(m.size for m in model.registry.get_masks())
 
   out = {
-      'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
-      'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+      'metric': cfg['metric'], 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-      'config': {'workload': 'ResNet-50 ImageNet-shaped, 80% ERK (54 masked tensors, 25.5M weights), '
-                             'batch 256/GPU, RigL drop 0.3 cosine every 100 steps, Nesterov momentum',
-                 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
+      'config': {'workload': cfg['workload'] + ', RigL drop 0.3 cosine every 100 steps, Nesterov momentum',
+                 'name': args.config, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
                  'l2_policy': 'inputs larger than L2 (activations per step >> 126 MB)',
                  'mask_updates_in_timed_region': n_updates,
+                 'masks_identical_across_replicas': masks_identical,
                  'cuda_graph': bool(graphed)},
       'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': 'images/sec', 'steps': e2e_steps,
@@ -258,25 +334,30 @@ def run_ours(args):
       'gpu_launches': int(launches),
       'mask_update_ms': mask_ms,
       'mask_update_algorithmic_GBps': 8.25 * total_w / mask_ms / 1e6,
-      'roofline': {'bound': 'tensor', 'kernel': 'k_igemm_kmajor2 / k_igemm_wgrad / k_halo3x3_* (all masked conv+linear launches)',
+      'roofline': {'bound': 'tensor',
+                   'kernel': 'k_igemm_kmajor2 / k_igemm_wgrad / k_halo3x3_* / k_stem_s2d_* (all masked conv+linear launches)',
                    'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved_tf / tf_peak,
+                   # the metric's own fraction: masked FLOPs of the whole job over the whole step (all kernels)
+                   'achieved_step': step_tf, 'frac_step': step_tf / (tf_peak * world),
                    'peak_source': peak_src + ' bf16_tflops_sustained',
-                   'algorithmic_gflop_per_image': ALG_GFLOP_PER_IMAGE,
-                   'dense_executed_tflops': DENSE_GFLOP_PER_IMAGE * BATCH / conv_ms,
+                   'algorithmic_gflop_per_image': alg,
+                   'dense_executed_gflop_per_image': flops['dense_executed_gflop'],
+                   'dense_executed_tflops': flops['dense_executed_gflop'] * batch / conv_ms,
                    'conv_ms_per_step': conv_ms, 'conv_launches_per_step': n_conv_launch,
-                   'ms_per_step_by_kind': per_kind, 'traffic': _recorded_traffic()},
+                   'ms_per_step_by_kind': per_kind, 'traffic': _recorded_traffic(args.config)},
   }
   if world == 1 and not args.no_cpu_baseline:
-    out['cpu_baseline'] = cpu_baseline_leg(sample_batch=args.cpu_batch)
+    out['cpu_baseline'] = cpu_baseline_leg(args.config, sample_batch=args.cpu_batch)
   _emit(out)
   if dist is not None:
     dist.destroy_process_group()
 
 
-def _cpu_port_timing(batch, steps, warmup):
+def _cpu_port_timing(cfg_name, batch, steps, warmup):
   """Times the CPU port in a FRESH interpreter whose OpenMP environment is not the one
   torchrun exports (OMP_NUM_THREADS=1): torch then sizes its intra-op pool to the host's
-  cores.  Returns {'sec_per_step', 'mask_update_sec', 'threads'}."""
+  cores.  Returns {'times' (s per step, every timed step), 'mask_update_sec', 'threads'}."""
+  cfg = CONFIGS[cfg_name]
   env = dict(os.environ)
   for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OMP_PROC_BIND', 'OMP_PLACES', 'GOMP_CPU_AFFINITY',
             'KMP_AFFINITY', 'CUDA_VISIBLE_DEVICES'):
@@ -284,10 +365,11 @@ def _cpu_port_timing(batch, steps, warmup):
   env['CUDA_VISIBLE_DEVICES'] = ''
   code = ('import json,sys,torch; sys.path.insert(0, %r); '
           'from oracle import cpu_train_step as c; '
-          's, net, dense = c.time_train_steps(%d, %d, warmup=%d); '
+          'times, net, dense = c.time_train_steps_model(%r, %d, %d, warmup=%d, image_hw=%d, sparsity=%r); '
           'mu = c.time_mask_update(net, dense); '
-          'print("CPUPORT " + json.dumps({"sec_per_step": s, "mask_update_sec": mu, '
-          '"threads": torch.get_num_threads()}))' % (ROOT, batch, steps, warmup))
+          'print("CPUPORT " + json.dumps({"times": times, "mask_update_sec": mu, '
+          '"threads": torch.get_num_threads()}))' % (ROOT, cfg['model'], batch, steps, warmup, cfg['image'],
+                                                     cfg['sparsity']))
   out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=1500)
   for line in out.stdout.splitlines():
@@ -296,14 +378,25 @@ def _cpu_port_timing(batch, steps, warmup):
   raise RuntimeError('CPU port failed: ' + out.stderr[-2000:])
 
 
-def cpu_baseline_leg(sample_batch=16, steps=1):
+def _spread(times, batch):
+  t = np.asarray(times, np.float64)
+  return {'median_images_per_sec': batch / float(np.median(t)),
+          'p10_images_per_sec': batch / float(np.percentile(t, 90)),     # slow steps -> low throughput
+          'p90_images_per_sec': batch / float(np.percentile(t, 10)),
+          'timed_steps': int(t.size)}
+
+
+def cpu_baseline_leg(cfg_name, sample_batch=16, steps=5):
   """Times the CPU port of the reference path on the host cores (bounded sample)."""
-  t = _cpu_port_timing(sample_batch, steps, 1)
-  return {'value': sample_batch / t['sec_per_step'], 'unit': 'images/sec', 'cores': t['threads'], 'kind': 'port',
-          'sample': 'ResNet-50 80%% ERK fp32 train step (fwd + dense&masked bwd + momentum), batch %d, '
-                    '%d timed step(s) after 1 warm-up, torch-CPU port of the TF1 graph' % (sample_batch, steps),
+  t = _cpu_port_timing(cfg_name, sample_batch, steps, 1)
+  sp = _spread(t['times'], sample_batch)
+  return {'value': sp['median_images_per_sec'], 'unit': 'images/sec', 'cores': t['threads'], 'kind': 'port',
+          'sample': '%s fp32 train step (fwd + dense&masked bwd + momentum), batch %d, %d timed steps after 1 '
+                    'warm-up (median), torch-CPU port of the TF1 graph' % (CONFIGS[cfg_name]['workload'], sample_batch,
+                                                                        steps),
+          'spread': sp,
           'mask_update_ms': t['mask_update_sec'] * 1e3,
-          'mask_update_sample': 'one drop/grow update of all 54 layers (numpy stable argsort x2 per layer)'}
+          'mask_update_sample': 'one drop/grow update of all masked layers (numpy stable argsort x2 per layer)'}
 
 
 def run_reference(args):
@@ -312,22 +405,24 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  cfg = CONFIGS[args.config]
   batch = args.cpu_batch
-  steps = max(1, min(args.steps, 3))
-  warm = max(1, min(args.warmup, 1))
+  steps = max(5, min(args.steps, 8))         # >= 5 timed steps: a 3-step sample was too noisy
+  warm = max(1, min(args.warmup, 2))
   t0 = time.perf_counter()
-  t = _cpu_port_timing(batch, steps, warm)
-  sec, mu, threads = t['sec_per_step'], t['mask_update_sec'], t['threads']
-  value = batch / sec
+  t = _cpu_port_timing(args.config, batch, steps, warm)
+  sp = _spread(t['times'], batch)
+  value = sp['median_images_per_sec']
   _emit({
-      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/sec',
-      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3,
+      'impl': 'reference', 'metric': cfg['metric'], 'value': value, 'unit': 'images/sec',
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': batch / value * 1e3,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': 'ResNet-50 ImageNet-shaped, 80%% ERK, CPU port of the reference TF1 train step, '
-                             'bounded sample of batch %d per step' % batch},
-      'cpu_baseline': {'value': value, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
-                       'sample': 'batch %d, %d step(s), wall %.1fs' % (batch, steps, time.perf_counter() - t0)},
-      'mask_update_ms': mu * 1e3,
+      'config': {'workload': '%s, CPU port of the reference TF1 train step, bounded sample of batch %d per step'
+                             % (cfg['workload'], batch), 'name': args.config},
+      'cpu_baseline': {'value': value, 'unit': 'images/sec', 'cores': t['threads'], 'kind': 'port',
+                       'sample': 'batch %d, %d timed steps (median), wall %.1fs' % (batch, steps, time.perf_counter() - t0),
+                       'spread': sp},
+      'mask_update_ms': t['mask_update_sec'] * 1e3,
       'e2e': {'value': value, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0})
 
@@ -357,6 +452,7 @@ def main():
   ap.add_argument('--steps', type=int, default=100)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
   ap.add_argument('--cpu-batch', type=int, default=16)
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--layer-report', default=None)

@@ -98,6 +98,13 @@ typedef struct {
 #define RIGL_LAYER_GROW_SCORE_SIGNED 1  /* rank score_grow verbatim (signed), as `_get_update_op(score_drop,
                                            score_grow, ...)` (base.py:276-343) does with caller-built scores,
                                            e.g. the rigl_tf2 updaters' -|g|; default ranks |score_grow| */
+#define RIGL_LAYER_DROP_ONLY 2          /* grow nothing: mask <- the kept set (top n_ones - n_prune of the drop
+                                           scores); weights and slots are not touched */
+#define RIGL_LAYER_ALL_ACTIVE 4         /* rank EVERY position as if the mask were all ones (n_ones = n).  With
+                                           DROP_ONLY and n_prune_override = get_n_zeros(n, sparsity) this is the
+                                           "mask = top-k of a score" of SparseSnipOptimizer (|g*w|, score_drop) and
+                                           SparseDNWOptimizer (|w|: no score_drop), sparse_optimizers.py:286-316,
+                                           :436-465 */
 
 typedef enum {
   RIGL_GROW_ZEROS = 0,       /* 'zeros'            base.py:372-373 */
@@ -144,6 +151,20 @@ RIGL_API size_t rigl_packed_weights_bytes(int taps, int cin, int cout);
  * cin_pad / cout_pad = rounded up to a multiple of 8 (16-byte rows); padding = 0. */
 RIGL_API int rigl_pack_masked_weights(const float* w_hwio, const uint32_t* mask_bits, int taps,
                                       int cin, int cout, void* packed, void* stream);
+
+/* The same for ALL masked layers of a model in ONE launch (the reference rebuilds every layer's
+ * `mask * weights` once per step; per-layer launches cost more than the 200 MB they move).  Pointers are
+ * captured at plan creation, like rigl_mask_plan.  Not capturable: create (allocates); capturable: run. */
+typedef struct {
+  const float* weights;        /* [taps][cin][cout] fp32 (HWIO / [in,out]) */
+  const uint32_t* mask_bits;   /* [rigl_mask_words(taps*cin*cout)] */
+  void* packed;                /* rigl_packed_weights_bytes(taps, cin, cout) bytes, 256B aligned */
+  int32_t taps, cin, cout, reserved;
+} rigl_pack_desc;
+typedef struct rigl_pack_plan rigl_pack_plan;
+RIGL_API int rigl_pack_plan_create(const rigl_pack_desc* layers, int n_layers, rigl_pack_plan** out);
+RIGL_API int rigl_pack_plan_destroy(rigl_pack_plan* plan);
+RIGL_API int rigl_pack_plan_run(rigl_pack_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------
  * Masked conv2d / linear as implicit GEMM (tcgen05 on sm_100a; a CUDA-core

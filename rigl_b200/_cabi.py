@@ -22,6 +22,11 @@ class LayerDesc(C.Structure):
               ('n', C.c_int64), ('n_prune_override', C.c_int32), ('flags', C.c_int32), ('grad', C.c_void_p)]
 
 
+class PackDesc(C.Structure):
+  _fields_ = [('weights', C.c_void_p), ('mask_bits', C.c_void_p), ('packed', C.c_void_p),
+              ('taps', C.c_int32), ('cin', C.c_int32), ('cout', C.c_int32), ('reserved', C.c_int32)]
+
+
 class ConvDesc(C.Structure):
   _fields_ = [('batch', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('cin', C.c_int32),
               ('out_h', C.c_int32), ('out_w', C.c_int32), ('cout', C.c_int32),
@@ -29,7 +34,7 @@ class ConvDesc(C.Structure):
 
 
 GROW_ZEROS, GROW_TENSOR, GROW_GRAD_SCALE, GROW_GRAD_SIGN = 0, 1, 2, 3
-LAYER_GROW_SCORE_SIGNED = 1
+LAYER_GROW_SCORE_SIGNED, LAYER_DROP_ONLY, LAYER_ALL_ACTIVE = 1, 2, 4
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 
@@ -50,6 +55,9 @@ SIGNATURES = {
     'rigl_mask_plan_read_stats': (C.c_int, [_vp, _vp, C.POINTER(C.c_int32), _vp]),
     'rigl_packed_weights_bytes': (_sz, [_i32, _i32, _i32]),
     'rigl_pack_masked_weights': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'rigl_pack_plan_create': (C.c_int, [C.POINTER(PackDesc), _i32, C.POINTER(_vp)]),
+    'rigl_pack_plan_destroy': (C.c_int, [_vp]),
+    'rigl_pack_plan_run': (C.c_int, [_vp, _vp]),
     'rigl_conv_workspace_bytes': (_sz, [C.POINTER(ConvDesc)]),
     'rigl_masked_conv2d_fprop': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rigl_bn_partial_rows': (C.c_int, []),

@@ -70,10 +70,12 @@ def build(force=False, verbose=False):
     failed = failed or p.returncode != 0
   if failed:
     raise RuntimeError('nvcc failed building librigl_b200.so')
-  link = [nvcc_path(), '-shared', '-o', LIB] + objs + ['-cudart', 'static', '-Xcompiler', '-fPIC']
+  tmp = LIB + '.tmp.%d' % os.getpid()       # link aside, then rename: a concurrent reader never sees a partial file
+  link = [nvcc_path(), '-shared', '-o', tmp] + objs + ['-cudart', 'static', '-Xcompiler', '-fPIC']
   r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   if r.returncode != 0:
     raise RuntimeError('link failed:\n' + r.stdout)
+  os.replace(tmp, LIB)
   with open(STAMP, 'w') as f:
     f.write(digest)
   return LIB

@@ -165,37 +165,47 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
                                 partial + (size_t)blockIdx.x * 2 * C, red);
 }
 
-// Sums partial[b][which][c] over b for a 32-channel slab: blockDim = (32 channels, 32 slices).
-__device__ __forceinline__ void slab_sums(const float* __restrict__ partial, int nblocks, int C, int c,
+// Sums partial[b][which][c] over b for an 8-channel slab with 1024 threads: lane = (channel c = lane & 7,
+// sub-slice lane >> 3), slice = 4 * warp + sub (128 slices), so a C-channel layer runs C/8 CTAs (the reduction is
+// L2-latency bound: what matters is how many loads are in flight, not bytes) and every load instruction fetches
+// full 32-byte sectors.  fp64 accumulation in a fixed order: deterministic.
+constexpr int kFinCh = 8, kFinSlices = 128;
+__device__ __forceinline__ bool slab_sums(const float* __restrict__ partial, int nblocks, int C, int* c_out,
                                           double* s_out, double* q_out) {
-  __shared__ double sm_s[32][33], sm_q[32][33];
+  __shared__ double sm_s[32][kFinCh], sm_q[32][kFinCh];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * kFinCh + (lane & 7);
+  const int slice = 4 * warp + (lane >> 3);
   double s = 0.0, q = 0.0;
   if (c < C) {
-    // 8 rows (16 independent loads) in flight per thread: the loop is L2-latency bound, not bandwidth bound.
-    int b = threadIdx.y;
-    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
-      float vs[8], vq[8];
+    int b = slice;
+    for (; b + 3 * kFinSlices < nblocks; b += 4 * kFinSlices) {
+      float vs[4], vq[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        vs[u] = __ldg(partial + (size_t)(b + u * 32) * 2 * C + c);
-        vq[u] = __ldg(partial + (size_t)(b + u * 32) * 2 * C + C + c);
+      for (int u = 0; u < 4; ++u) {
+        vs[u] = __ldcg(partial + (size_t)(b + u * kFinSlices) * 2 * C + c);
+        vq[u] = __ldcg(partial + (size_t)(b + u * kFinSlices) * 2 * C + C + c);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { s += (double)vs[u]; q += (double)vq[u]; }
+      for (int u = 0; u < 4; ++u) { s += (double)vs[u]; q += (double)vq[u]; }
     }
-    for (; b < nblocks; b += 32) {
-      s += (double)partial[(size_t)b * 2 * C + c];
-      q += (double)partial[(size_t)b * 2 * C + C + c];
+    for (; b < nblocks; b += kFinSlices) {
+      s += (double)__ldcg(partial + (size_t)b * 2 * C + c);
+      q += (double)__ldcg(partial + (size_t)b * 2 * C + C + c);
     }
   }
-  sm_s[threadIdx.y][threadIdx.x] = s;
-  sm_q[threadIdx.y][threadIdx.x] = q;
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane < 8) { sm_s[warp][lane] = s; sm_q[warp][lane] = q; }
   __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int j = 1; j < 32; ++j) { s += sm_s[j][threadIdx.x]; q += sm_q[j][threadIdx.x]; }
-    *s_out = s;
-    *q_out = q;
-  }
+  if (threadIdx.x >= kFinCh) return false;
+  s = 0.0; q = 0.0;
+  for (int w = 0; w < 32; ++w) { s += sm_s[w][threadIdx.x]; q += sm_q[w][threadIdx.x]; }
+  *s_out = s; *q_out = q; *c_out = c;
+  return c < C;
 }
 
 // Forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running stats.
@@ -204,10 +214,9 @@ k_bn_finalize_fwd(const float* __restrict__ partial, int nblocks, int C, long lo
                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean,
                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift,
                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  int c;
   double s, q;
-  slab_sums(partial, nblocks, C, c, &s, &q);
-  if (threadIdx.y != 0 || c >= C) return;
+  if (!slab_sums(partial, nblocks, C, &c, &s, &q)) return;
   const double m = s / (double)rows;
   double var = q / (double)rows - m * m;
   if (var < 0.0) var = 0.0;
@@ -230,10 +239,9 @@ __global__ void __launch_bounds__(1024)
 k_bn_finalize_bwd(const float* __restrict__ partial, int nblocks, int C, long long rows,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef /*[2][C]: P, Q*/) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  int c;
   double s, q;
-  slab_sums(partial, nblocks, C, c, &s, &q);
-  if (threadIdx.y != 0 || c >= C) return;
+  if (!slab_sums(partial, nblocks, C, &c, &s, &q)) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
   const double c0 = s / (double)rows, c1 = q / (double)rows;
@@ -679,7 +687,7 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels,
       rpb, partial);
   RIGL_LAUNCH_CHECK("k_bn_colsum<0>");
-  k_bn_finalize_fwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, nb, channels, rows, eps, gamma, beta,
+  k_bn_finalize_fwd<<<(channels + kFinCh - 1) / kFinCh, 1024, 0, s>>>(partial, nb, channels, rows, eps, gamma, beta,
                                                                   save_mean, save_rstd, save_scale, save_shift,
                                                                   running_mean, running_var, momentum);
   RIGL_LAUNCH_CHECK("k_bn_finalize_fwd");
@@ -706,7 +714,7 @@ extern "C" int rigl_bn_forward_train_partials(const void* y, const void* residua
   RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0 && partial_rows > 0,
                "rigl_bn_forward_train_partials: bad sizes");
   cudaStream_t s = (cudaStream_t)stream_;
-  k_bn_finalize_fwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, partial_rows, channels, rows, eps, gamma,
+  k_bn_finalize_fwd<<<(channels + kFinCh - 1) / kFinCh, 1024, 0, s>>>(partial, partial_rows, channels, rows, eps, gamma,
                                                                   beta, save_mean, save_rstd, save_scale, save_shift,
                                                                   running_mean, running_var, momentum);
   RIGL_LAUNCH_CHECK("k_bn_finalize_fwd");
@@ -797,7 +805,7 @@ extern "C" int rigl_bn_backward2(const void* da, const void* da2, const void* y,
         save_shift, relu, rows, channels, rpb, partial);
     RIGL_LAUNCH_CHECK("k_bn_colsum<1>");
   }
-  k_bn_finalize_bwd<<<(channels + 31) / 32, dim3(32, 32), 0, s>>>(partial, nb, channels, rows, save_mean, save_rstd,
+  k_bn_finalize_bwd<<<(channels + kFinCh - 1) / kFinCh, 1024, 0, s>>>(partial, nb, channels, rows, save_mean, save_rstd,
                                                                   save_scale, dgamma, dbeta, coef);
   RIGL_LAUNCH_CHECK("k_bn_finalize_bwd");
   const long long nvec = rows * (channels / 8);

@@ -114,30 +114,39 @@ __device__ __forceinline__ bool build_live_mask(const IgemmParams& p, int n_tile
 // ----------------------------------------------------------------------------
 // fprop / dgrad kernel: D[128 pixels, BN] += A[128, 64] * B[BN, 64]^T per (tap, k block)
 // ----------------------------------------------------------------------------
-// Column sums of a 32(rows = lanes) x 32(columns = registers) fp32 block and of its squares by
-// recursive halving: 31 shuffles per statistic instead of 160; lane l ends up owning column l.
-__device__ __forceinline__ void warp_colsum_add(const uint32_t (&r)[32], float* __restrict__ bn_row, int co0, int n,
-                                                int lane, bool row_valid) {
-  // rows outside the pixel grid are NOT zero in general (their receptive field can still touch
-  // valid input), so they are masked here; the TMA store clips them independently.
-  float v[32], q[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) { v[j] = row_valid ? __uint_as_float(r[j]) : 0.f; q[j] = v[j] * v[j]; }
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      const float keep_v = upper ? v[j + s] : v[j], send_v = upper ? v[j] : v[j + s];
-      const float keep_q = upper ? q[j + s] : q[j], send_q = upper ? q[j] : q[j + s];
-      v[j] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, s);
-      q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, s);
-    }
+// Batch-norm statistics of one staged output slab (128 pixel rows x 64 channels, bf16, 128-byte rows with the
+// 16-byte chunks XOR-swizzled by row & 7 -- exactly what the TMA store is about to read): column sums and sums of
+// squares of the values AS STORED (bf16-rounded), added to this CTA's row of the partial table.
+//   warp q (0..3) owns channels 16q..16q+15 (chunks 2q, 2q+1); lane = (row group g = lane >> 3, channel pair
+//   cp = lane & 7); group g walks rows 32g + ((i + 2g) & 31), i = 0..31: the four groups then sit on four different
+//   swizzle phases, so the 32 lanes of every LDS.32 hit 32 different banks.
+// 32 LDS + ~130 FP ops per thread per slab, two shuffles per statistic, and ONE RED per (slab, channel, statistic):
+// each table entry is only ever touched by one lane of one warp, in tile order, so the fp32 sums are deterministic.
+// Rows outside the pixel grid are written as zeros by their owner (see the staging loops), so they do not count.
+__device__ __forceinline__ void slab_bn_stats(uint32_t slab, int quad, int lane, float* __restrict__ bn_row, int co0,
+                                              int n) {
+  const int cp = lane & 7, g = lane >> 3;
+  const uint32_t chunk = (uint32_t)(2 * quad + (cp >> 2));
+  const uint32_t word = (uint32_t)(cp & 3) * 4u;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t row = (uint32_t)(32 * g + ((i + 2 * g) & 31));
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slab + row * 128u + (((chunk ^ (row & 7u)) << 4) | word)));
+    const float a = __uint_as_float(v << 16), b = __uint_as_float(v & 0xffff0000u);
+    s0 += a; s1 += b;
+    q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
   }
-  const int co = co0 + lane;
-  if (co < n) {
-    atomicAdd(bn_row + co, v[0]);
-    atomicAdd(bn_row + n + co, q[0]);
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  const int co = co0 + 16 * quad + 2 * cp;
+  if (g == 0 && co < n) {          // (n is a multiple of 8 on this path, so co + 1 < n as well)
+    atomicAdd(bn_row + co, s0); atomicAdd(bn_row + co + 1, s1);
+    atomicAdd(bn_row + n + co, q0); atomicAdd(bn_row + n + co + 1, q1);
   }
 }
 
@@ -276,8 +285,6 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t slab_ctr = 0;
     float* bn_row = p.bn_partial ? p.bn_partial + (size_t)blockIdx.x * 2 * p.N : nullptr;
-    // (keeping the sums in registers across tiles needs the slab loop fully unrolled: measured
-    //  slower -- 255 registers, 2 ms more fprop time per step -- than one RED per column per tile)
     if (bn_row) {            // this CTA's row of the batch-norm partial sums starts at zero
       for (int i = (warp - 2) * 32 + lane; i < 2 * p.N; i += 128) bn_row[i] = 0.f;
       __threadfence_block();
@@ -310,10 +317,6 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0), r0);
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0 + 32), r1);
           tmem_ld_wait();
-          if (bn_row) {        // fused BN statistics: column sums over this warp's 32 rows, one RED per column
-            warp_colsum_add(r0, bn_row, co0, p.N, lane, pix_ok);
-            warp_colsum_add(r1, bn_row, co0 + 32, p.N, lane, pix_ok);
-          }
           const uint32_t row_addr = slab + (uint32_t)row * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -324,8 +327,8 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
               const float a = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
               const float b = __uint_as_float(e + 1 < 32 ? r0[e + 1] : r1[e + 1 - 32]);
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              pk[q] = *reinterpret_cast<uint32_t*>(&h);
-            }
+              pk[q] = pix_ok ? *reinterpret_cast<uint32_t*>(&h) : 0u;   // rows outside the grid: clipped by the
+            }                                                           // store, must be zero for the statistics
             const uint32_t dst = row_addr + (uint32_t)((j ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                          "r"(pk[3])
@@ -337,6 +340,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
             tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
+          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N);   // next to the bulk store's own read
           ++slab_ctr;
         }
       } else {
@@ -590,6 +594,12 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
     const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t slab_ctr = 0;
+    float* bn_row = p.bn_partial ? p.bn_partial + (size_t)blockIdx.x * 2 * p.N : nullptr;
+    if (bn_row) {            // this CTA's row of the batch-norm partial sums starts at zero
+      for (int i = (warp - 2) * 32 + lane; i < 2 * p.N; i += 128) bn_row[i] = 0.f;
+      __threadfence_block();
+      named_bar_sync(1, 128);
+    }
     for (int pair = cluster_id; pair < total_pairs; pair += n_clusters) {
       const int n_tile = pair % p.n_tiles;
       const int m_tile = (pair / p.n_tiles) * 2 + (int)cta_rank;
@@ -626,8 +636,8 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
               const float a = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
               const float b = __uint_as_float(e + 1 < 32 ? r0[e + 1] : r1[e + 1 - 32]);
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              pk[q] = *reinterpret_cast<uint32_t*>(&h);
-            }
+              pk[q] = pix_ok ? *reinterpret_cast<uint32_t*>(&h) : 0u;   // rows outside the grid: clipped by the
+            }                                                           // store, must be zero for the statistics
             const uint32_t dst = row_addr + (uint32_t)((j ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                          "r"(pk[3])
@@ -639,6 +649,7 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
             tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
+          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N);   // next to the bulk store's own read
           ++slab_ctr;
         }
       } else {
@@ -1032,7 +1043,7 @@ size_t tc_workspace_bytes(const ConvGeom& g) {
 
 // With the 2-CTA multicast each CTA fetches half of the weight tile (B box = bn_tile/2 rows).
 static bool kmajor_use_pair(const IgemmParams& p) {      // CTA-pair (cta_group::2) kernel
-  return g_cta_pair && p.bn_partial == nullptr && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
+  return g_cta_pair && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
 }
 static bool kmajor_use_mc(const IgemmParams& p) {
   return !kmajor_use_pair(p) && g_cluster_mc && p.tiles_w * p.tiles_h * p.tiles_n >= 2;
@@ -1042,7 +1053,7 @@ static int kmajor_b_rows(const IgemmParams& p, int bn_tile) {
 }
 
 static int kmajor_grid(const IgemmParams& p) {         // CTAs the K-major launcher will use (p.n_tiles set)
-  const int cl = kmajor_use_mc(p) ? 2 : 1;
+  const int cl = (kmajor_use_mc(p) || kmajor_use_pair(p)) ? 2 : 1;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int pairs = ((m_tiles + cl - 1) / cl) * p.n_tiles;
   int clusters = g_num_sms / cl;
@@ -1141,8 +1152,13 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   {
     HaloParams hp = {};
-    if (y != nullptr && y_f32 == nullptr && bias == nullptr && bn_partial == nullptr && halo_fprop_ok(g, &hp))
+    if (y != nullptr && y_f32 == nullptr && bias == nullptr && halo_fprop_ok(g, &hp)) {
+      if (bn_partial != nullptr) {        // the halo kernels have no statistics epilogue: the caller runs the plain
+        set_error("fused BN statistics: layer runs on the halo kernels");   // call + the stats pass instead
+        return RIGL_ERR_UNSUPPORTED;
+      }
       return halo_launch_kmajor(hp, x, g.cin, g.x_pitch, pk + L.off_fprop, L.cin_pad, g.cout, y, g.cout, false, s);
+    }
   }
   IgemmParams p = {};
   choose_box(g.out_w, g.out_h, g.batch, 128, &p.bw, &p.bh, &p.bn);

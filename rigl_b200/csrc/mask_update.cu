@@ -48,7 +48,8 @@ struct LayerState {     // 64 bytes, zeroed at the start of every run
   int32_t n_ones, n_prune, n_keep, n_cand_drop;
   int32_t n_cand_grow, drop_bucket, grow_bucket, n_ones_acc;
   uint32_t drop_need, grow_need, cand_cnt_drop, cand_cnt_grow;
-  uint32_t pad1[4];
+  int32_t n_grow;          // connections to grow: n_prune, or 0 with RIGL_LAYER_DROP_ONLY
+  uint32_t pad1[3];
 };
 
 struct LayerDev {
@@ -145,6 +146,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const bool has_noise = L.noise != nullptr && !explicit_score;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
+  const bool all_active = (L.flags & RIGL_LAYER_ALL_ACTIVE) != 0;     // rank every position (mask treated as ones)
   uint32_t zero_cnt = 0, ones = 0;
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;      // 32 groups per warp
@@ -170,7 +172,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
     for (int u = 0; u < kBatch; ++u) {
       if (!act[u]) continue;
       if ((lane & 7) == 0) ones += __popc(mw[u]);
-      const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
+      const uint32_t nib = all_active ? 0xFu : (mw[u] >> (4 * (lane & 7))) & 0xFu;
       const float ws4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
       const float ns4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
 #pragma unroll
@@ -269,7 +271,8 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   for (int b = threadIdx.x; b < kBins; b += kResolveThreads) hist[b] = __ldcg(gh + b);
   __syncthreads();
   if (threadIdx.x == kResolveThreads - 1) {
-    const int32_t n_ones = st->n_ones_acc;             // accumulated by k_hist_drop
+    const int32_t n_ones = (L.flags & RIGL_LAYER_ALL_ACTIVE) ? (int32_t)L.n
+                                                             : st->n_ones_acc;   // accumulated by k_hist_drop
     int32_t n_prune = L.n_prune_override >= 0
                           ? L.n_prune_override
                           : (int32_t)__fmul_rn((float)n_ones, prm.drop_fraction);  // base.py:287-289
@@ -280,6 +283,7 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     st->n_ones = n_ones;
     st->n_prune = n_prune;
     st->n_keep = n_ones - n_prune;
+    st->n_grow = (L.flags & RIGL_LAYER_DROP_ONLY) ? 0 : n_prune;
   }
   if (threadIdx.x == 0) { out[0] = kBins; out[1] = 0; out[2] = 0; }
   __syncthreads();
@@ -313,6 +317,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
   const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
+  const bool all_active = (L.flags & RIGL_LAYER_ALL_ACTIVE) != 0;
   uint32_t zero_cnt = 0;
   constexpr int kWarps = kScanThreads / 32;
   constexpr int kTrips = kChunk / kGroup / kWarps;
@@ -338,7 +343,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
     for (int u = 0; u < kBatch; ++u) {
       if (!act[u]) continue;
       const uint32_t e0 = bases[u] + 4 * lane;
-      const uint32_t nib = (mw[u] >> (4 * (lane & 7))) & 0xFu;
+      const uint32_t nib = all_active ? 0xFu : (mw[u] >> (4 * (lane & 7))) & 0xFu;
       const float ws4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
       const float gs4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
       const float ns4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
@@ -522,8 +527,8 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     // grow threshold bin: top-n_prune among positions with mask1 == 0
     if (tid == 0) { out[0] = kBins; out[1] = 0; out[2] = 0; }
     __syncthreads();
-    const uint32_t n_prune = (uint32_t)st->n_prune;
-    if (n_prune > 0) find_bin_desc<kBins>(ghist, n_prune, warp_sums, out);
+    const uint32_t n_grow = (uint32_t)st->n_grow;
+    if (n_grow > 0) find_bin_desc<kBins>(ghist, n_grow, warp_sums, out);
     if (tid == 0) {
       st->grow_bucket = (int32_t)out[0];
       st->grow_need = out[1];
@@ -550,7 +555,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
   uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + L.off_hist2_grow);
   uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand);
-  if (st->n_prune == 0) return;                       // nothing grows; mask1 is final
+  if (st->n_grow == 0) return;                        // nothing grows; mask1 is final
   const uint32_t bucket = (uint32_t)st->grow_bucket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n = L.n;

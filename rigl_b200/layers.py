@@ -26,8 +26,11 @@ from .masks import MaskVariable
 import ctypes as C
 
 _WS = {}
-FUSE_BN_STATS = False         # opt-in: the conv epilogue emits the following BN's batch statistics
-                              # (measured on R50 b256: the epilogue work costs what the stats pass saves)
+import os as _os
+# The conv epilogue emits the following BN's batch statistics (column sums / sums of squares of the bf16 output
+# slab it has just staged for the TMA store), so the BN forward needs no stats pass over the activation.
+# RIGL_FUSE_BN_STATS=0: separate stats pass.
+FUSE_BN_STATS = _os.environ.get('RIGL_FUSE_BN_STATS', '1') != '0'
 _BN_ROWS = []
 
 
@@ -38,7 +41,6 @@ def _bn_partial_rows():
 
 
 STEM_WINDOW_PATH = False     # route small-Cin convs through the window-tensor-map kernels
-import os as _os
 # space-to-depth halo kernels for the 7x7/2 3-channel stem (csrc/stem_s2d.cuh): validated on
 # B200 at the start of round 2 (tools/umma_sw32_probe.cu + tests/test_conv_gpu.py::test_conv_stem_s2d_path);
 # RIGL_STEM_S2D=0 falls back to the patch-matrix (im2col) stem
@@ -125,6 +127,69 @@ def pack_ahead(layers):
       l.pack()
       _PACKED_AHEAD.add(id(l))
   _PACK_JOIN[dev] = True
+
+
+class PackPlan(object):
+  """ONE launch packing the operands of a fixed list of layers (rigl_pack_plan_*): `mask * W` -> bf16 GEMM
+  operands + tile survivor counts for every layer.  Raw pointers are captured, so the plan is rebuilt whenever a
+  weight / bitmap / blob is reallocated."""
+
+  def __init__(self):
+    self._plan, self._key = C.c_void_p(None), None
+
+  def __del__(self):
+    try:
+      self._destroy()
+    except Exception:
+      pass
+
+  def _destroy(self):
+    if self._plan and self._plan.value:
+      _cabi.lib().rigl_pack_plan_destroy(self._plan)
+      self._plan = C.c_void_p(None)
+
+  @staticmethod
+  def _entries(layer):
+    """(weights ptr, bitmap ptr, blob ptr, taps, cin, cout) of every generic blob `layer.pack()` would write."""
+    if getattr(layer, 'patch_mode', False):
+      return [(layer.weight.data_ptr(), layer.mask.bits.data_ptr(), layer.packed_patch.data_ptr(), 1, layer._kdim,
+               layer._cout)]
+    return [(layer.weight.data_ptr(), layer.mask.bits.data_ptr(), layer.packed.data_ptr(), layer._taps, layer._cin,
+             layer._cout)]
+
+  def run(self, layers):
+    ents = [e for l in layers for e in self._entries(l)]
+    key = tuple(ents)
+    if key != self._key:
+      self._destroy()
+      descs = (_cabi.PackDesc * len(ents))()
+      for d, (w, b, pk, taps, cin, cout) in zip(descs, ents):
+        d.weights, d.mask_bits, d.packed, d.taps, d.cin, d.cout = w, b, pk, taps, cin, cout
+      plan = C.c_void_p(None)
+      _cabi.check(_cabi.lib().rigl_pack_plan_create(descs, len(ents), C.byref(plan)), 'rigl_pack_plan_create')
+      self._plan, self._key = plan, key
+    _cabi.check(_cabi.lib().rigl_pack_plan_run(self._plan, _cabi.stream_ptr()), 'rigl_pack_plan_run')
+    for l in layers:          # the small special-format stem operands are not part of the batch
+      if getattr(l, 's2d_mode', False) or getattr(l, 'smallc_mode', False):
+        l.pack_special()
+
+
+_PACK_PLANS = {}
+
+
+def pack_all(layers):
+  """Packs the operands of all `layers` with one launch on the current stream; their forward passes then skip
+  the per-layer pack for this step."""
+  layers = [l for l in layers if l.weight.is_cuda]
+  if not layers:
+    return
+  key = tuple(id(l) for l in layers)
+  plan = _PACK_PLANS.get(key)
+  if plan is None:
+    plan = _PACK_PLANS[key] = PackPlan()
+  plan.run(layers)
+  for l in layers:
+    _PACKED_AHEAD.add(id(l))
 
 
 def _pack_for_forward(layer):
@@ -304,6 +369,13 @@ class SparseConv2d(_MaskedLayer):
       _cabi.check(_cabi.lib().rigl_pack_masked_weights(
           self.weight.data_ptr(), self.mask.bits.data_ptr(), 1, self._kdim, self._cout,
           self.packed_patch.data_ptr(), _cabi.stream_ptr()), 'rigl_pack_masked_weights')
+      self.pack_special()
+    else:
+      super(SparseConv2d, self).pack()
+
+  def pack_special(self):
+    """The stem's own operand formats (space-to-depth / window kernels)."""
+    if self.patch_mode:
       if self.s2d_mode:
         d = self._desc(1, 16, 16)
         _cabi.check(_cabi.lib().rigl_stem_s2d_pack_weights(
@@ -314,8 +386,6 @@ class SparseConv2d(_MaskedLayer):
         _cabi.check(_cabi.lib().rigl_smallc_pack_weights(
             d, self.weight.data_ptr(), self.mask.bits.data_ptr(), self.packed_smallc.data_ptr(),
             _cabi.stream_ptr()), 'rigl_smallc_pack_weights')
-    else:
-      super(SparseConv2d, self).pack()
 
   @property
   def pad(self):

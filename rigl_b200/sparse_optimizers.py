@@ -119,3 +119,158 @@ class SparseMomentumOptimizer(SparseSETOptimizer):
 
   def _score_grow_for(self, mask, weights):
     return self._ema[weights.name]              # |.| is taken in the kernel
+
+
+class _TopKMaskAssigner(object):
+  """`mask <- top-(n - get_n_zeros(n, sparsity)) of a per-position score` for every layer at once -- the
+  `mask_fn` SNIP and DNW hand to sparse_utils.get_mask_init_fn (reference :286-316, :436-465: a full top_k sort
+  per layer, ties -> lower index) -- on the batched select kernels: the drop phase alone
+  (RIGL_LAYER_DROP_ONLY), ranking every position (RIGL_LAYER_ALL_ACTIVE), n_prune = get_n_zeros."""
+
+  def _init_topk(self, default_sparsity, mask_init_method, custom_sparsity_map):
+    from .masks import MaskUpdateEngine
+    self._default_sparsity = default_sparsity
+    self._mask_init_method = mask_init_method
+    self._custom_sparsity_map = custom_sparsity_map or {}
+    self._topk_engine = MaskUpdateEngine()
+    self._sparsities = None
+
+  def layer_sparsities(self):
+    from . import sparse_utils
+    if self._sparsities is None:      # depends on the (static) mask shapes only
+      self._sparsities = sparse_utils.get_sparsities(self.get_masks(), self._mask_init_method,
+                                                     self._default_sparsity, self._custom_sparsity_map)
+    return self._sparsities
+
+  def _assign_topk(self, scores):
+    """scores: per layer an explicit float32 score tensor, or None to rank |weights| in-kernel."""
+    from . import _cabi, sparse_utils
+    sp = self.layer_sparsities()
+    specs = []
+    for m, w, sc in zip(self.get_masks(), self.get_weights(), scores):
+      flat_w = w.data.view(-1)
+      spec = dict(mask=m, weights=flat_w, score_grow=flat_w,        # (score_grow is not read: nothing grows)
+                  n_prune=int(sparse_utils.get_n_zeros(m.size, sp[m.name])),
+                  flags=_cabi.LAYER_DROP_ONLY | _cabi.LAYER_ALL_ACTIVE)
+      if sc is not None:
+        spec['score_drop'] = sc.contiguous().view(-1)
+      specs.append(spec)
+    if specs:
+      self._topk_engine.run(specs, 0.0)
+
+
+class SparseSnipOptimizer(PruningGetterTorchMixin, _TopKMaskAssigner):
+  """SNIP (Lee et al.): at global step 0 -- instead of an optimizer step -- every mask becomes the top
+  (1 - sparsity) fraction of |grad * weight|; afterwards a plain wrapper (reference :217-337)."""
+
+  def __init__(self, optimizer, default_sparsity, mask_init_method, custom_sparsity_map=None,
+               use_locking=False, use_tpu=False, name='SparseSnipOptimizer'):
+    self._optimizer = optimizer
+    self._use_tpu = use_tpu
+    self._name = name
+    self._init_topk(default_sparsity, mask_init_method, custom_sparsity_map)
+    self.is_snipped = False                    # the reference's non-trainable `is_snipped` variable
+
+  @property
+  def param_groups(self):
+    return self._optimizer.param_groups
+
+  def zero_grad(self, set_to_none=False):
+    self._optimizer.zero_grad(set_to_none=set_to_none)
+    for mw in self.get_masked_weights():
+      mw.fresh = False
+
+  def compute_gradients(self, loss, **kwargs):
+    self.zero_grad(set_to_none=kwargs.get('set_to_none', False))
+    loss.backward()
+    return [(p.grad, p) for g in self._optimizer.param_groups for p in g['params']]
+
+  def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+    import torch
+    gs = global_step if global_step is not None else sparse_opt_base.get_or_create_global_step()
+    if int(gs) == 0 and not self.is_snipped:
+      by_var = {id(v): g for g, v in (grads_and_vars or [])}
+      scores = []
+      for w in self.get_weights():
+        g = by_var.get(id(w), w.grad)
+        if g is None:
+          raise ValueError('SNIP needs a gradient for %s' % w.name)
+        g = g.detach().to(torch.float32)
+        if self._use_tpu and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1:
+          g = g.clone()
+          torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)      # tpu_ops.cross_replica_sum
+        scores.append((g * w.data).abs_())
+      self._assign_topk(scores)
+      self.is_snipped = True
+      return True
+    sparse_opt_base.SparseSETOptimizerBase._install_grads(grads_and_vars)
+    self._optimizer.step()
+    if global_step is not None:
+      global_step.increment()
+    return False
+
+  def minimize(self, loss, global_step=None, **kwargs):
+    return self.apply_gradients(self.compute_gradients(loss, **kwargs), global_step=global_step)
+
+  def state_dict(self):
+    return {'optimizer': self._optimizer.state_dict(), 'is_snipped': bool(self.is_snipped)}
+
+  def load_state_dict(self, sd):
+    self._optimizer.load_state_dict(sd['optimizer'])
+    self.is_snipped = bool(sd['is_snipped'])
+
+
+class SparseDNWOptimizer(PruningGetterTorchMixin, _TopKMaskAssigner):
+  """Discovering Neural Wirings (Wortsman et al.): the weights are updated with the DENSE gradient
+  (dL/d(mask*w) applied to w) and after EVERY optimizer step each mask becomes the top (1 - sparsity) fraction
+  of |w| (reference :340-480)."""
+
+  def __init__(self, optimizer, default_sparsity, mask_init_method, custom_sparsity_map=None, use_tpu=False,
+               use_locking=False, name='SparseDNWOptimizer'):
+    self._optimizer = optimizer
+    self._use_tpu = use_tpu
+    self._name = name
+    self._init_topk(default_sparsity, mask_init_method, custom_sparsity_map)
+
+  @property
+  def param_groups(self):
+    return self._optimizer.param_groups
+
+  def zero_grad(self, set_to_none=False):
+    self._optimizer.zero_grad(set_to_none=set_to_none)
+    for mw in self.get_masked_weights():
+      mw.fresh = False
+
+  def compute_gradients(self, loss, var_list=None, **kwargs):
+    """Gradients with every masked variable replaced by its masked_weights tensor (replace_with_masked_weights,
+    :388-396), i.e. the DENSE gradient, handed back under the weight variable (:398-408)."""
+    self.zero_grad(set_to_none=kwargs.get('set_to_none', False))
+    loss.backward()
+    for w, mw in zip(self.get_weights(), self.get_masked_weights()):
+      dense = mw.dense_grad.view(w.shape)
+      if w.grad is None:
+        w.grad = dense.clone()
+      else:
+        w.grad.copy_(dense)
+    params = var_list if var_list is not None else [p for g in self._optimizer.param_groups for p in g['params']]
+    return [(p.grad, p) for p in params]
+
+  def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+    sparse_opt_base.SparseSETOptimizerBase._install_grads(grads_and_vars)
+    self._optimizer.step()
+    if global_step is not None:
+      global_step.increment()
+    self._assign_topk([None] * len(self.get_masks()))       # |w| is ranked in-kernel
+    for mw in self.get_masked_weights():
+      mw.fresh = False
+    return True
+
+  def minimize(self, loss, global_step=None, **kwargs):
+    return self.apply_gradients(self.compute_gradients(loss, **kwargs), global_step=global_step)
+
+  def state_dict(self):
+    return {'optimizer': self._optimizer.state_dict()}
+
+  def load_state_dict(self, sd):
+    self._optimizer.load_state_dict(sd['optimizer'])

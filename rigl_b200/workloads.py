@@ -295,8 +295,8 @@ class TrainHarness(object):
       mw.fresh = False
     self.inner.zero_grad(set_to_none=set_to_none)
     if getattr(self, '_overlap', False) and getattr(self, '_pack_ahead', False):
-      # every layer but the first packs its operands on the side stream while the stem runs
-      layers.pack_ahead(self.model.registry.layers()[1:])
+      # ONE launch packs the operands (mask * W -> bf16, both layouts) of every layer
+      layers.pack_all(self.model.registry.layers())
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
     layers.WGRAD_SIDE_STREAM = bool(getattr(self, '_overlap', False))

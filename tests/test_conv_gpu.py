@@ -244,3 +244,113 @@ def test_conv_single_cta_mma_path(case):
   env = dict(os.environ, RIGL_CTA_PAIR='0')
   out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   assert 'ONE_OK' in out.stdout, out.stdout[-1500:]
+
+
+# ---- BASELINE-size problems (C2: ResNet-50, batch 256, 224x224): many more tiles than CTAs, so the persistent
+# loops' TMEM double buffering, smem-ring wrap and split-K schedules run for many tiles per CTA.
+def _r50_erk80_sparsity():
+  layers = orc.resnet50_masked_layers()
+  sp = orc.get_sparsities([orc.FakeMask(n + '/mask:0', sh) for n, sh, _, _ in layers], 'erdos_renyi_kernel', 0.8, {})
+  return layers, sp
+
+
+def _r50_b256_shapes():
+  """Distinct (n,h,w,cin,cout,k,stride,sparsity) of the 53 ResNet-50 convs at batch 256."""
+  layers, sp = _r50_erk80_sparsity()
+  seen, out = set(), []
+  for name, sh, stride, out_hw in layers:
+    if len(sh) != 4:
+      continue
+    k, _, cin, cout = sh
+    key = (out_hw * stride, cin, cout, k, stride)
+    if key in seen:
+      continue
+    seen.add(key)
+    out.append((256, out_hw * stride, out_hw * stride, cin, cout, k, stride, round(float(sp[name + '/mask:0']), 3)))
+  return out
+
+
+# the four shapes VERDICT r1 asked for: 56^2 64->256 1x1, 56^2->28^2 128 3x3 s2, 14^2 256 3x3, 7^2 512 3x3
+_B256_ORACLE = [c for c in _r50_b256_shapes() if (c[1], c[3], c[4], c[5], c[6]) in
+                ((56, 64, 256, 1, 1), (56, 128, 128, 3, 2), (14, 256, 256, 3, 1), (7, 512, 512, 3, 1))]
+
+
+@pytest.mark.parametrize('case', _B256_ORACLE, ids=lambda c: 'h%d_c%d_%d_k%d_s%d' % (c[1], c[3], c[4], c[5], c[6]))
+def test_conv_b256_baseline_shapes_vs_fp64_oracle(case):
+  assert len(_B256_ORACLE) == 4
+  _conv_case(case, force_simt=False)
+
+
+def _run_both(layer, x, dy, force_simt):
+  _cabi.lib().rigl_set_force_simt(1 if force_simt else 0)
+  try:
+    xx = x.detach().clone().requires_grad_(True)
+    layer.masked_weights.fresh = False
+    layer.weight.grad = None
+    y = layer(xx)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    return y.detach().float(), xx.grad.detach().float() if xx.grad is not None else None, \
+        layer.masked_weights.dense_grad.clone()
+  finally:
+    _cabi.lib().rigl_set_force_simt(0)
+
+
+@pytest.mark.parametrize('case', _r50_b256_shapes(), ids=lambda c: 'h%d_c%d_%d_k%d_s%d' % (c[1], c[3], c[4], c[5], c[6]))
+def test_conv_b256_every_r50_shape_tensor_core_vs_cuda_core(case):
+  """Every distinct ResNet-50 conv shape at batch 256: the tcgen05 kernels against the shape-agnostic CUDA-core
+  kernels on the SAME device inputs and packed operands (fp32 accumulation on both sides; bf16 outputs may differ
+  by one rounding)."""
+  n, h, w, cin, cout, k, stride, sparsity = case
+  rng = np.random.RandomState(cin * 7 + cout + k)
+  pruning.reset_default_registry()
+  layer = SparseConv2d(cin, cout, k, strides=stride, padding='FIXED', name='t', device=DEV)
+  layer.mask.assign(orc.get_mask_random_numpy((k, k, cin, cout), sparsity, rng).astype(np.float32))
+  g = torch.Generator(device=DEV).manual_seed(cin + cout)
+  x = torch.randn((n, cin, h, w), device=DEV, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  ho = layer.out_size(h)[0]
+  dy = torch.randn((n, cout, ho, ho), device=DEV, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  y1, dx1, dw1 = _run_both(layer, x, dy, force_simt=False)
+  y0, dx0, dw0 = _run_both(layer, x, dy, force_simt=True)
+  for got, want, what in ((y1, y0, 'fprop'), (dx1, dx0, 'dgrad')):
+    scale = float(want.abs().max())
+    bad = (got - want).abs() > want.abs() * 2.0 ** -7 + scale * 2e-5
+    assert not bool(bad.any()), '%s %s: %d elements off, max err %g (scale %g)' % (
+        what, case, int(bad.sum()), float((got - want).abs().max()), scale)
+  scale = float(dw0.abs().max())
+  assert float((dw1 - dw0).abs().max()) <= 5e-5 * scale, 'wgrad %s: %g vs scale %g' % (
+      case, float((dw1 - dw0).abs().max()), scale)
+
+
+def test_batched_pack_equals_per_layer_pack():
+  """layers.pack_all (ONE launch over a tile table) writes byte-identical operand blobs -- both K-major layouts and
+  the 64x64 survivor counts -- to the per-layer rigl_pack_masked_weights calls, incl. ragged channel counts, the
+  stem's patch-matrix form and a linear layer."""
+  from rigl_b200 import layers
+  pruning.reset_default_registry()
+  rng = np.random.RandomState(5)
+  ls = [SparseConv2d(3, 64, 7, strides=2, padding='FIXED', name='stem', device=DEV),
+        SparseConv2d(64, 256, 1, name='a', device=DEV), SparseConv2d(72, 40, 3, name='ragged', device=DEV),
+        SparseConv2d(128, 128, 3, strides=2, name='b', device=DEV), SparseLinear(300, 100, name='fc', device=DEV),
+        SparseConv2d(5, 3, 3, name='tiny', device=DEV)]
+  for l in ls:
+    l.mask.assign(orc.get_mask_random_numpy(tuple(l.weight.shape), 0.8, rng).astype(np.float32))
+  blobs = lambda l: [b for b in (getattr(l, 'packed_patch', None), l.packed, getattr(l, 'packed_s2d', None)) if b is not None]
+  want = []
+  for l in ls:
+    for b in blobs(l):
+      b.fill_(0x5a)
+    l.pack()
+    want.append([b.clone() for b in blobs(l)])
+  for l in ls:
+    for b in blobs(l):
+      b.fill_(0xa5)
+  layers.pack_all(ls)
+  torch.cuda.synchronize()
+  for l, ws in zip(ls, want):
+    got = blobs(l)
+    if getattr(l, 'patch_mode', False):       # patch-mode layers only pack their patch / special forms
+      got, ws = [got[0]] + got[2:], [ws[0]] + ws[2:]
+    for g, w in zip(got, ws):
+      assert torch.equal(g, w), l.scope
+  layers._PACKED_AHEAD.clear()

@@ -288,3 +288,71 @@ def test_get_update_op_uses_scores_verbatim():
   want = orc.get_update_op(sd, sg, m, w, np.float32(0.5))
   assert np.array_equal(layer.mask.numpy(), want['mask'])
   assert layer.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes()
+
+
+# ---- SparseSnipOptimizer / SparseDNWOptimizer on the batched select kernels, against the masks produced by
+# EXECUTING the reference's apply_gradients (tests/golden/snip_dnw_golden.json, tools/make_golden_snip_dnw.py).
+import json as _json
+import os as _os
+
+with open(_os.path.join(_os.path.dirname(__file__), 'golden', 'snip_dnw_golden.json')) as _f:
+  _SNIP_DNW = _json.load(_f)
+
+
+def _gdec(e):
+  return np.frombuffer(bytes.fromhex(e['hex']), dtype=np.dtype(e['dtype'])).reshape(e['shape']).copy()
+
+
+@pytest.mark.parametrize('case', _SNIP_DNW['cases'], ids=[c['tag'] for c in _SNIP_DNW['cases']])
+def test_snip_dnw_product_path_on_reference_executed_golden(case):
+  from rigl_b200.layers import SparseConv2d
+  pruning.reset_default_registry()
+  layers_ = []
+  for i, sh in enumerate(case['shapes'], 1):
+    if len(sh) == 2:
+      l = SparseLinear(sh[0], sh[1], use_bias=False, name='layer%d' % i, device=DEV)
+    else:
+      l = SparseConv2d(sh[2], sh[3], sh[0], name='layer%d' % i, device=DEV)
+    with torch.no_grad():
+      l.weight.copy_(torch.from_numpy(_gdec(case['weights'][i - 1])).to(DEV))
+    layers_.append(l)
+  params = [l.weight for l in layers_]
+  inner = torch.optim.SGD(params, lr=0.0)                      # the golden generator's inner optimizer is a no-op
+  gs = GlobalStep(0 if case['kind'] == 'snip' else 3)
+  if case['kind'] == 'snip':
+    so = sparse_optimizers.SparseSnipOptimizer(inner, case['sparsity'], case['method'], custom_sparsity_map=case['custom'])
+    gv = [(torch.from_numpy(_gdec(g)).to(DEV), p) for g, p in zip(case['grads'], params)]
+    assert so.apply_gradients(gv, global_step=gs) is True and so.is_snipped and gs.value == 0
+    masks = [l.mask.numpy().copy() for l in layers_]
+    assert so.apply_gradients(gv, global_step=gs) is False and gs.value == 1      # already snipped: plain step
+    assert all(np.array_equal(a, l.mask.numpy()) for a, l in zip(masks, layers_))
+  else:
+    so = sparse_optimizers.SparseDNWOptimizer(inner, case['sparsity'], case['method'], custom_sparsity_map=case['custom'])
+    gv = [(torch.zeros_like(p), p) for p in params]
+    so.apply_gradients(gv, global_step=gs)
+    assert gs.value == 4
+    masks = [l.mask.numpy() for l in layers_]
+  for i, (got, l) in enumerate(zip(masks, layers_)):
+    want = _gdec(case['masks'][i])
+    assert np.array_equal(got, want), (case['tag'], i)
+    assert l.weight.detach().cpu().numpy().tobytes() == _gdec(case['weights'][i]).tobytes()    # weights untouched
+
+
+def test_dnw_trains_with_dense_gradient_and_tracks_topk():
+  """DNW end to end on a real layer: the weight update uses the DENSE gradient (masked-out weights move too) and
+  after every step the mask equals the oracle's top-|w| mask of the UPDATED weights."""
+  pruning.reset_default_registry()
+  torch.manual_seed(5)
+  layer = SparseLinear(48, 40, use_bias=False, name='layer1', device=DEV, out_dtype=torch.float32)
+  layer.mask.assign(orc.get_mask_random_numpy((48, 40), 0.75, np.random.RandomState(5)))
+  inner = torch.optim.SGD(layer.parameters(), lr=0.1)
+  so = sparse_optimizers.SparseDNWOptimizer(inner, 0.75, 'random')
+  gs = GlobalStep(0)
+  x, t = torch.randn(16, 48, device=DEV), torch.randn(16, 40, device=DEV)
+  for _ in range(3):
+    m0, w0 = layer.mask.numpy().copy(), layer.weight.detach().cpu().numpy().copy()
+    so.minimize(((layer(x) - t) ** 2).mean(), gs)
+    w1 = layer.weight.detach().cpu().numpy()
+    assert np.abs((w1 - w0)[m0 == 0]).max() > 0                  # masked-out weights received the dense gradient
+    assert np.array_equal(layer.mask.numpy(), orc.dnw_mask(w1, 0.75))
+  assert gs.value == 3

@@ -1,0 +1,166 @@
+"""Whole-train-step parity: ONE CUDA sparse train step against the CPU restatement of the reference's step
+(oracle/cpu_train_step.py), for the three model families of BASELINE.json (ResNet-50 C2/C3, WRN-22-2 C5,
+MobileNet-v1 C4), plus bit-identical masks / re-initialised weights / momentum slots after the mask updates.
+
+What is compared and how tight it can be ("whole-step bound"):
+  * The oracle runs the whole network in fp32 (like the reference's CPU path); the CUDA path stores every
+    activation and activation gradient in bf16 (fp32 accumulation inside each conv / BN reduction), as BASELINE
+    C2 prescribes.  A dense gradient therefore carries ~2^-9 relative rounding per bf16 tensor on the path from
+    the loss to that layer and back through the saved activations, ~50 tensors deep for ResNet-50, amplified by
+    small-batch batch norm.  The north-star's 1e-5 applies to a single op on fp32 accumulators
+    (tests/test_conv_gpu.py); the attainable whole-step bound is a relative L2 error of a few per cent per
+    layer.  The bounds below are 3x what was MEASURED on a B200 (recorded by this test into
+    gpurun_out/whole_step_parity_<model>.json when that directory exists); a wrong tap, stride, padding,
+    transposed operand, BN statistic or residual wiring gives errors of order 1.
+  * Mask updates are integer work: given the dense gradients the CUDA step produced, the oracle's drop/grow
+    (base.py:276-343 restated) must give BIT-IDENTICAL masks, weights and momentum slots.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu_train_step as cpu
+from oracle import rigl_oracle as orc
+from rigl_b200 import workloads
+from rigl_b200.norm import FusedBatchNormReLU
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _bn_init(seed):
+  def init(key, c):
+    r = np.random.RandomState((__import__('zlib').crc32(key.encode()) ^ seed) & 0x7fffffff)
+    return (0.5 + r.rand(c)).astype(np.float32), (0.1 * r.standard_normal(c)).astype(np.float32)
+  return init
+
+
+def _load(model, net):
+  """Copies the oracle net's masked weights / masks / BN parameters into the CUDA model (BNs in execution order,
+  which is the registration order in both)."""
+  with torch.no_grad():
+    for l in model.registry.layers():
+      l.weight.copy_(net.w[l.scope].to(DEV))
+      l.mask.assign(net.m[l.scope].numpy())
+    bns = [m for m in model.modules() if isinstance(m, FusedBatchNormReLU)]
+    assert len(bns) == len(net.bn_order)
+    for mod, key in zip(bns, net.bn_order):
+      g, b = net.bn[key]
+      mod.weight.copy_(g.detach().to(DEV))
+      mod.bias.copy_(b.detach().to(DEV))
+
+
+def _rel_l2(got, want):
+  return float(np.linalg.norm(got.astype(np.float64) - want.astype(np.float64)) /
+               (np.linalg.norm(want.astype(np.float64)) + 1e-30))
+
+
+def _record(tag, payload):
+  if os.path.isdir('gpurun_out'):
+    with open(os.path.join('gpurun_out', 'whole_step_parity_%s.json' % tag), 'w') as f:
+      json.dump(payload, f, indent=1)
+
+
+def _compare_step(tag, model, net, images, labels, harness, loss_tol, grad_tol, label_smoothing):
+  x32 = images.float()
+  want_loss, want_dense = net.forward_backward(x32, labels) if label_smoothing is None else \
+      net.forward_backward(x32, labels, label_smoothing=label_smoothing)
+  _load(model, net)
+  xd = images.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  yd = labels.to(DEV)
+  got_loss = float(harness._forward_backward(xd, yd, set_to_none=False))
+  torch.cuda.synchronize()
+  rel = {}
+  for l in model.registry.layers():
+    got = l.masked_weights.dense_grad.view(l.weight.shape).cpu().numpy()
+    want = want_dense[l.scope].numpy()
+    rel[l.scope] = _rel_l2(got, want)
+    # masked gradient = mask * dense, exactly
+    m = net.m[l.scope].numpy()
+    assert np.array_equal(l.weight.grad.cpu().numpy(), got * m), l.scope
+  worst = max(rel, key=rel.get)
+  _record(tag, dict(loss_cuda=got_loss, loss_oracle=want_loss, rel_l2=rel, worst=worst))
+  assert abs(got_loss - want_loss) <= loss_tol * abs(want_loss), (got_loss, want_loss)
+  assert rel[worst] <= grad_tol, 'dense grad of %s: rel L2 %.4f (median %.4f)' % (
+      worst, rel[worst], float(np.median(list(rel.values()))))
+  return rel
+
+
+def _check_update_steps(model, harness, images, labels, n_steps, expect_updates):
+  """Runs `n_steps` public train steps; at every mask-update step the oracle's drop/grow on the SAME dense
+  gradients / noise must reproduce masks, weights and momentum slots bit for bit."""
+  xd = images.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  yd = labels.to(DEV)
+  layers = model.registry.layers()
+  updates = []
+  for step in range(n_steps):
+    before = []
+    for l in layers:
+      st = harness.inner.state.get(l.weight, {})
+      mom = st.get('momentum_buffer')
+      before.append((l.mask.numpy().copy(), l.weight.detach().cpu().numpy().copy(),
+                     None if mom is None else mom.detach().cpu().numpy().copy()))
+    gs = harness.global_step.value
+    harness.step(xd, yd)
+    torch.cuda.synchronize()
+    if not harness.opt.last_update_was_mask_update:
+      assert harness.global_step.value == gs + 1
+      continue
+    assert harness.global_step.value == gs            # RigL: no optimizer step on update iterations
+    updates.append(gs)
+    frac = np.float32(harness.opt.drop_fraction)
+    for l, (m0, w0, mom0) in zip(layers, before):
+      dense = l.masked_weights.dense_grad.view(l.weight.shape).cpu().numpy()
+      noise = harness.opt._noise_bufs[l.weight.name].view(l.weight.shape).cpu().numpy()
+      want = orc.rigl_mask_update(m0, w0, dense, frac, noise=noise, slots=[] if mom0 is None else [mom0])
+      assert np.array_equal(l.mask.numpy(), want['mask']), (gs, l.scope)
+      assert l.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes(), (gs, l.scope)
+      if mom0 is not None:
+        got_mom = harness.inner.state[l.weight]['momentum_buffer'].cpu().numpy()
+        assert got_mom.tobytes() == want['slots'][0].tobytes(), (gs, l.scope)
+  assert updates == expect_updates, updates
+
+
+def test_resnet50_step_vs_cpu_oracle():
+  torch.manual_seed(0)
+  net = cpu.CpuResNet50(sparsity=0.8, seed=11, bf16_weights=True)
+  net.bn_init = _bn_init(11)
+  model = workloads.ResNet50(device=DEV)
+  images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
+  labels = torch.randint(0, 1000, (8,))
+  h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
+  _compare_step('resnet50', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=None)
+  _check_update_steps(model, h, images, labels, 4, [0, 2])
+
+
+def test_wrn22_2_step_vs_cpu_oracle():
+  torch.manual_seed(1)
+  net = cpu.CpuWideResNet(depth=22, width=2, sparsity=0.95, seed=12, bf16_weights=True)
+  net.bn_init = _bn_init(12)
+  model = workloads.WideResNet(depth=22, width=2, droprate=0.0, device=DEV)
+  with torch.no_grad():
+    model.conv_1.weight.copy_(net.p['conv_1'].detach().permute(3, 2, 0, 1).to(DEV))
+  images = torch.randn(16, 3, 32, 32).to(torch.bfloat16)
+  labels = torch.randint(0, 10, (16,))
+  h = workloads.TrainHarness(model, lr=0.05, weight_decay=5e-4, label_smoothing=0.0, frequency=2, end_step=100)
+  _compare_step('wrn22_2', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=0.0)
+  _check_update_steps(model, h, images, labels, 4, [0, 2])
+
+
+def test_mobilenet_v1_step_vs_cpu_oracle():
+  torch.manual_seed(2)
+  net = cpu.CpuMobileNetV1(sparsity=0.9, seed=13, bf16_weights=True)
+  net.bn_init = _bn_init(13)
+  model = workloads.MobileNetV1(device=DEV)
+  with torch.no_grad():
+    model.initial_conv.weight.copy_(net.p['initial_conv'].detach().permute(3, 2, 0, 1).to(DEV))
+    for i, blk in enumerate(model.blocks):
+      blk.depthwise.weight.copy_(net.p['depthwise_%d' % i].detach().to(DEV))
+  images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
+  labels = torch.randint(0, 1000, (8,))
+  h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
+  _compare_step('mobilenet_v1', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=0.1)
+  _check_update_steps(model, h, images, labels, 4, [0, 2])
