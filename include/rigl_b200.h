@@ -167,6 +167,29 @@ RIGL_API int rigl_pack_plan_destroy(rigl_pack_plan* plan);
 RIGL_API int rigl_pack_plan_run(rigl_pack_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Wrapped-optimizer step with the masked gradient fused in.
+ * Replaces tf.train.MomentumOptimizer(use_nesterov=True).apply_gradients on
+ * dL/dweights = mask * dL/d(mask*weights) (imagenet_train_eval.py:355-365,
+ * sparse_optimizers_base.py:478-485) for EVERY parameter of a model in one launch:
+ *   g = (bit ? grad * grad_scale : 0) + weight_decay * w;  accum = momentum * accum + g;
+ *   w -= lr * (nesterov ? g + momentum * accum : accum).
+ * The learning rate is read from device memory (graph replays follow a schedule).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  float* param;                /* [n] in/out */
+  float* momentum;             /* [n] in/out accumulator (the 'momentum' slot of the reference) */
+  const float* grad;           /* [n] gradient; the DENSE gradient when mask_bits != NULL */
+  const uint32_t* mask_bits;   /* NULL (dense parameter) or the layer's bitmap */
+  int64_t n;
+  float weight_decay;
+  float grad_scale;            /* multiplies grad (1/replicas for the summed dense gradients) */
+} rigl_sgd_desc;
+typedef struct rigl_sgd_plan rigl_sgd_plan;
+RIGL_API int rigl_sgd_plan_create(const rigl_sgd_desc* params, int n_params, rigl_sgd_plan** out);
+RIGL_API int rigl_sgd_plan_destroy(rigl_sgd_plan* plan);
+RIGL_API int rigl_sgd_plan_run(rigl_sgd_plan* plan, const float* lr_dev, float momentum, int nesterov, void* stream);
+
+/* ------------------------------------------------------------------------
  * Masked conv2d / linear as implicit GEMM (tcgen05 on sm_100a; a CUDA-core
  * kernel serves shapes whose row pitch is not a 16-byte multiple).
  * Replaces layers.masked_conv2d / masked_fully_connected fprop and its two

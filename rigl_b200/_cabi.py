@@ -27,6 +27,11 @@ class PackDesc(C.Structure):
               ('taps', C.c_int32), ('cin', C.c_int32), ('cout', C.c_int32), ('reserved', C.c_int32)]
 
 
+class SgdDesc(C.Structure):
+  _fields_ = [('param', C.c_void_p), ('momentum', C.c_void_p), ('grad', C.c_void_p), ('mask_bits', C.c_void_p),
+              ('n', C.c_int64), ('weight_decay', C.c_float), ('grad_scale', C.c_float)]
+
+
 class ConvDesc(C.Structure):
   _fields_ = [('batch', C.c_int32), ('in_h', C.c_int32), ('in_w', C.c_int32), ('cin', C.c_int32),
               ('out_h', C.c_int32), ('out_w', C.c_int32), ('cout', C.c_int32),
@@ -58,6 +63,9 @@ SIGNATURES = {
     'rigl_pack_plan_create': (C.c_int, [C.POINTER(PackDesc), _i32, C.POINTER(_vp)]),
     'rigl_pack_plan_destroy': (C.c_int, [_vp]),
     'rigl_pack_plan_run': (C.c_int, [_vp, _vp]),
+    'rigl_sgd_plan_create': (C.c_int, [C.POINTER(SgdDesc), _i32, C.POINTER(_vp)]),
+    'rigl_sgd_plan_destroy': (C.c_int, [_vp]),
+    'rigl_sgd_plan_run': (C.c_int, [_vp, _vp, _f32, _i32, _vp]),
     'rigl_conv_workspace_bytes': (_sz, [C.POINTER(ConvDesc)]),
     'rigl_masked_conv2d_fprop': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rigl_bn_partial_rows': (C.c_int, []),

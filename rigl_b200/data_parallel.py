@@ -33,6 +33,7 @@ class DataParallel(object):
     self.flat_dense = None
     self.flat_other = None
     self._others = []
+    self.masked_grads_in_optimizer = False   # the fused optimizer forms mask * dense / world itself
 
   # -- setup ------------------------------------------------------------------
   def attach(self, model):
@@ -74,6 +75,8 @@ class DataParallel(object):
     for l in model.registry.layers():
       g = l.masked_weights.dense_grad
       g.rigl_reduced = True
+      if self.masked_grads_in_optimizer:
+        continue
       if l.weight.grad is None:
         l.weight.grad = torch.empty_like(l.weight)
       l.mask.apply_to(g, out=l.weight.grad.view(-1), scale=scale)

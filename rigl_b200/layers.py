@@ -95,6 +95,10 @@ def _workspace(device, nbytes):
 # the weight gradient is then written straight into `weight.grad` on the side stream instead of
 # being returned to autograd, and the caller must `join_side_streams()` after `backward()`.
 WGRAD_SIDE_STREAM = False
+# Set by TrainHarness around backward() when the inner optimizer is optim.FusedMomentumSGD: it forms
+# mask * dense_grad while loading the dense gradient, so the layers neither compute nor return the masked
+# weight gradient (`weight.grad` stays untouched).
+MASKED_GRAD_IN_OPTIMIZER = False
 _WS_SLOT = ['main']
 _SIDE = {}
 _SIDE_KEEP = []        # tensors the side stream may still be reading (released at the join)
@@ -256,7 +260,8 @@ class _MaskedConvFn(torch.autograd.Function):
     mw = layer.masked_weights
     gw = None
     if WGRAD_SIDE_STREAM and x.is_cuda and not Profiler.enabled:
-      if ctx.needs_input_grad[1] and layer.weight.grad is None:
+      want_gw = ctx.needs_input_grad[1] and not MASKED_GRAD_IN_OPTIMIZER
+      if want_gw and layer.weight.grad is None:
         layer.weight.grad = torch.zeros_like(layer.weight)
       patch_keep = getattr(layer, '_patch_cache', None)     # (the stem's patch matrix is dropped inside _wgrad)
       main, side = torch.cuda.current_stream(x.device), side_stream(x.device)
@@ -265,7 +270,7 @@ class _MaskedConvFn(torch.autograd.Function):
       try:
         with torch.cuda.stream(side):
           layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh)
-          if ctx.needs_input_grad[1]:
+          if want_gw:
             layer.mask.apply_to(mw.dense_grad, out=layer.weight.grad.view(-1))
       finally:
         _WS_SLOT[0] = 'main'
@@ -276,7 +281,7 @@ class _MaskedConvFn(torch.autograd.Function):
       _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
       mw.fresh = True
       mw.dense_grad.rigl_reduced = False
-      if ctx.needs_input_grad[1]:
+      if ctx.needs_input_grad[1] and not MASKED_GRAD_IN_OPTIMIZER:
         gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
     gb = None
     if ctx.has_bias and ctx.needs_input_grad[2]:

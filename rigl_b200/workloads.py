@@ -25,6 +25,14 @@ BATCH_NORM_DECAY = 0.9
 BATCH_NORM_EPSILON = 1e-5
 
 
+class DenseConv2d(nn.Conv2d):
+  """An un-masked conv of the reference models (WRN `conv_1`, MobileNet `initial_conv` / depthwise): float32
+  master weights like every TF variable, bf16 compute (stock cuDNN kernels -- not a masked op)."""
+
+  def forward(self, x):
+    return F.conv2d(x, self.weight.to(torch.bfloat16), None, self.stride, self.padding, self.dilation, self.groups)
+
+
 def _BNReLU(channels, relu=True, init_zero=False, device='cuda'):
   """batch_norm_relu (resnet_model.py:41-80) on the fused streaming kernels (csrc/bn.cu)."""
   return FusedBatchNormReLU(channels, relu=relu, init_zero=init_zero, eps=BATCH_NORM_EPSILON,
@@ -121,7 +129,7 @@ class WideResNet(nn.Module):
       raise ValueError('Depth of ResNet specified not sufficient.')
     self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
     reg, n_blocks = self.registry, (depth - 4) // 6
-    self.conv_1 = nn.Conv2d(3, 16, 3, padding=1, bias=False, device=device, dtype=torch.bfloat16)
+    self.conv_1 = DenseConv2d(3, 16, 3, padding=1, bias=False, device=device)
     self.droprate = droprate
     blocks, cin = [], 16
     for name, size, subsample in (('conv_2', 16 * width, False), ('conv_3', 32 * width, True),
@@ -172,13 +180,12 @@ class MobileNetV1(nn.Module):
     super(MobileNetV1, self).__init__()
     self.registry = registry if registry is not None else pruning.MaskedLayerRegistry()
     reg = self.registry
-    self.initial_conv = nn.Conv2d(3, 32, 3, stride=2, padding=1, bias=False, device=device, dtype=torch.bfloat16)
+    self.initial_conv = DenseConv2d(3, 32, 3, stride=2, padding=1, bias=False, device=device)
     self.initial_bn = _BNReLU(32, device=device)
     blocks, cin = [], 32
     for i, (filters, stride) in enumerate(self.CFG):
       blk = nn.Module()
-      blk.depthwise = nn.Conv2d(cin, cin, 3, stride=stride, padding=1, groups=cin, bias=False, device=device,
-                                dtype=torch.bfloat16)
+      blk.depthwise = DenseConv2d(cin, cin, 3, stride=stride, padding=1, groups=cin, bias=False, device=device)
       blk.bn_dw = _BNReLU(cin, device=device)
       blk.pointwise = SparseConv2d(cin, filters, 1, strides=1, padding='FIXED',
                                    name='resnet_model/contraction_1x1_%d' % i, device=device, registry=reg)
@@ -233,11 +240,27 @@ class TrainHarness(object):
 
   def __init__(self, model, lr=0.1, momentum=0.9, weight_decay=1e-4, label_smoothing=0.1,
                drop_fraction=0.3, drop_fraction_anneal='cosine', begin_step=0, end_step=25000,
-               frequency=100, data_parallel=None, optimizer_cls=SparseRigLOptimizer):
+               frequency=100, data_parallel=None, optimizer_cls=SparseRigLOptimizer, lr_schedule=None,
+               fused_optimizer=None):
+    """lr_schedule: optional callable(global_step) -> learning rate, evaluated on the host before every step
+    (optim.make_imagenet_lr_fn is the reference's, imagenet_train_eval.py:317-354); `lr` is then only the
+    initial value.  fused_optimizer: the inner optimizer is optim.FusedMomentumSGD (one launch, mask * dense_grad
+    fused in, device-resident learning rate); default on for CUDA models (RIGL_FUSED_SGD=0 -> torch.optim.SGD)."""
+    import os
     self.model = model
     self.label_smoothing = label_smoothing
-    self.inner = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, nesterov=True,
-                                 weight_decay=weight_decay, foreach=True)
+    self.lr_schedule = lr_schedule
+    on_cuda = next(model.parameters()).is_cuda
+    if fused_optimizer is None:
+      fused_optimizer = on_cuda and os.environ.get('RIGL_FUSED_SGD', '1') != '0'
+    self.fused = bool(fused_optimizer)
+    if self.fused:
+      from .optim import FusedMomentumSGD
+      self.inner = FusedMomentumSGD(model.parameters(), lr=lr, momentum=momentum, nesterov=True,
+                                    weight_decay=weight_decay)
+    else:
+      self.inner = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, nesterov=True,
+                                   weight_decay=weight_decay, foreach=True)
     self.opt = optimizer_cls(self.inner, begin_step, end_step, frequency, drop_fraction=drop_fraction,
                              drop_fraction_anneal=drop_fraction_anneal,
                              use_tpu=data_parallel is not None).bind(model.registry)
@@ -245,6 +268,26 @@ class TrainHarness(object):
     self.dp = data_parallel
     if self.dp is not None:
       self.dp.attach(model)
+    if self.fused:
+      # masked layers: the optimizer reads dense_grad (+ bitmap) directly; under data parallelism the buffers
+      # hold the SUM over replicas, the weight update takes the mean (CrossShardOptimizer)
+      self.inner.attach_masked_layers(model.registry.layers(),
+                                      grad_scale=1.0 / self.dp.world if self.dp is not None else 1.0)
+      if self.dp is not None:
+        self.dp.masked_grads_in_optimizer = True
+
+  def _apply_lr_schedule(self):
+    if self.lr_schedule is None:
+      return
+    lr = float(self.lr_schedule(self.global_step.value))
+    if self.fused:
+      self.inner.set_lr(lr)
+    else:
+      if getattr(self, 'graphed', False) and lr != self.inner.param_groups[0]['lr']:
+        raise RuntimeError('torch.optim.SGD bakes the learning rate into a captured graph: use the fused optimizer '
+                           'with an lr schedule')
+      for g in self.inner.param_groups:
+        g['lr'] = lr
 
   # ---- CUDA-graph mode: the forward+backward and the inner optimizer step are captured once and
   # replayed (inter-kernel launch gaps and all host work disappear); the data-parallel
@@ -279,6 +322,8 @@ class TrainHarness(object):
       self.graph_kernel_launches = _cabi.launch_count() - before     # rigl kernels inside one replay
       self.replayed_kernel_launches = 0
       self._g_opt = torch.cuda.CUDAGraph()
+      if self.fused:
+        self.inner.prepare()                   # slots / device lr / launch plan: allocated OUTSIDE the capture
       with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
         self.inner.step()
       self.graphed = True
@@ -300,14 +345,17 @@ class TrainHarness(object):
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
     layers.WGRAD_SIDE_STREAM = bool(getattr(self, '_overlap', False))
+    layers.MASKED_GRAD_IN_OPTIMIZER = self.fused      # mask * dense_grad is formed inside the optimizer kernel
     try:
       loss.backward()
     finally:
       layers.WGRAD_SIDE_STREAM = False
+      layers.MASKED_GRAD_IN_OPTIMIZER = False
       layers.join_side_streams()                # (no-op when nothing was forked)
     return loss
 
   def _graphed_step(self, images, labels):
+    self._apply_lr_schedule()
     self._sx.copy_(images, non_blocking=True)
     self._sy.copy_(labels, non_blocking=True)
     self._g_fb.replay()
@@ -328,6 +376,8 @@ class TrainHarness(object):
     """images: bf16 [N,3,H,W] channels_last; labels: int64 [N].  Returns the loss tensor."""
     if getattr(self, 'graphed', False):
       return self._graphed_step(images, labels)
+    self._apply_lr_schedule()
+    from . import layers
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
     # without DP the grads are re-created by autograd (no zero-fill, no accumulate pass);
@@ -335,7 +385,11 @@ class TrainHarness(object):
     self.inner.zero_grad(set_to_none=self.dp is None)
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
-    loss.backward()
+    layers.MASKED_GRAD_IN_OPTIMIZER = self.fused
+    try:
+      loss.backward()
+    finally:
+      layers.MASKED_GRAD_IN_OPTIMIZER = False
     if self.dp is not None:
       self.dp.reduce_gradients(self.model)
     self.opt.collect_masked_grads()

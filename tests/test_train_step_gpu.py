@@ -61,7 +61,7 @@ def test_train_steps_update_semantics_and_conservation():
   model = workloads.ResNet50(device=DEV)
   workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=2)
   ones_before = [m.count_ones() for m in model.registry.get_masks()]
-  h = workloads.TrainHarness(model, lr=0.05, frequency=3, end_step=100)
+  h = workloads.TrainHarness(model, lr=0.05, frequency=3, end_step=100, fused_optimizer=False)   # (weight.grad is read below)
   x = torch.randn(8, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   y = torch.randint(0, 1000, (8,), device=DEV)
   incs, losses = [], []
@@ -160,25 +160,63 @@ def test_cuda_graph_mode_matches_eager():
     assert a.sum() == b.sum()
 
 
-def test_cuda_graph_wgrad_side_stream_matches_serial_backward():
+@pytest.mark.parametrize('fused', [False, True])
+def test_cuda_graph_wgrad_side_stream_matches_serial_backward(fused):
   """In graph mode the dense wgrad kernels run on a forked stream (layers.WGRAD_SIDE_STREAM) next to the
   BN-backward chain.  Every kernel is deterministic, so replaying the captured forward+backward must
   reproduce the serial eager backward BIT FOR BIT (a missing dependency or a recycled buffer would not)."""
   torch.manual_seed(3)
   model = workloads.ResNet50(num_classes=10, device=DEV)
   workloads.init_masks(model, 'erdos_renyi_kernel', 0.8, seed=3)
-  h = workloads.TrainHarness(model, lr=0.1)
+  h = workloads.TrainHarness(model, lr=0.1, fused_optimizer=fused)
   x = torch.randn(8, 3, 64, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   y = torch.randint(0, 10, (8,), device=DEV)
   h._forward_backward(x, y, set_to_none=False)            # serial reference (no fork: _overlap is unset)
   torch.cuda.synchronize()
   layers_ = model.registry.layers()
   ref_dense = [l.masked_weights.dense_grad.clone() for l in layers_]
-  ref_grad = [l.weight.grad.clone() for l in layers_]
+  # (with the fused inner optimizer mask * dense_grad is formed inside the step kernel: no weight.grad)
+  ref_grad = [None if fused else l.weight.grad.clone() for l in layers_]
   assert h.enable_cuda_graph(x, y, overlap_wgrad=True) and h._overlap
   for _ in range(3):
     h._g_fb.replay()
     torch.cuda.synchronize()
     for l, d, g in zip(layers_, ref_dense, ref_grad):
       assert torch.equal(l.masked_weights.dense_grad, d), l.scope
-      assert torch.equal(l.weight.grad, g), l.scope
+      assert (l.weight.grad is None) if fused else torch.equal(l.weight.grad, g), l.scope
+
+
+def test_fused_momentum_sgd_matches_torch_sgd_on_the_same_gradients():
+  """optim.FusedMomentumSGD (one launch, mask * dense_grad formed in-kernel, device-resident lr) against
+  torch.optim.SGD(nesterov, weight_decay) fed the materialised masked gradients: same trajectories up to fp32
+  fma contraction, masked-out weights only decay, momentum slots agree, an lr change takes effect."""
+  from rigl_b200 import pruning
+  from rigl_b200.layers import SparseLinear
+  from rigl_b200.optim import FusedMomentumSGD
+  pruning.reset_default_registry()
+  torch.manual_seed(9)
+  la = SparseLinear(130, 77, name='a', device=DEV)          # 10010 weights: not a multiple of 4 -> scalar tail
+  lb = SparseLinear(130, 77, name='b', device=DEV)
+  rng = np.random.RandomState(9)
+  m = (rng.rand(130, 77) > 0.7).astype(np.float32)
+  la.mask.assign(m); lb.mask.assign(m)
+  with torch.no_grad():
+    lb.weight.copy_(la.weight); lb.bias.copy_(la.bias)
+  fused = FusedMomentumSGD(la.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-2)
+  fused.attach_masked_layers([la], grad_scale=0.5)
+  ref = torch.optim.SGD(lb.parameters(), lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-2)
+  for step in range(5):
+    dense = torch.randn(130 * 77, device=DEV)
+    gb = torch.randn(77, device=DEV)
+    la.masked_weights.dense_grad.copy_(dense)
+    la.bias.grad = gb.clone()
+    lb.weight.grad = (dense.view(130, 77) * torch.from_numpy(m).to(DEV) * 0.5)
+    lb.bias.grad = gb.clone()
+    if step == 3:
+      fused.set_lr(0.01)
+      ref.param_groups[0]['lr'] = 0.01
+    fused.step(); ref.step()
+    for pa, pb in ((la.weight, lb.weight), (la.bias, lb.bias)):
+      assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6), step
+      assert torch.allclose(fused.state[pa]['momentum_buffer'], ref.state[pb]['momentum_buffer'], rtol=1e-5, atol=1e-6)
+  assert la.weight.grad is None
