@@ -99,6 +99,9 @@ WGRAD_SIDE_STREAM = False
 # mask * dense_grad while loading the dense gradient, so the layers neither compute nor return the masked
 # weight gradient (`weight.grad` stays untouched).
 MASKED_GRAD_IN_OPTIMIZER = False
+# data_parallel.DataParallel while a backward pass should launch its bucketed all-reduces (set by TrainHarness):
+# `layer_done(layer, stream)` is called right after a layer's dense wgrad has been issued on `stream`.
+DP_HOOK = None
 _WS_SLOT = ['main']
 _SIDE = {}
 _SIDE_KEEP = []        # tensors the side stream may still be reading (released at the join)
@@ -181,6 +184,13 @@ class PackPlan(object):
 _PACK_PLANS = {}
 
 
+class _AllLayers(object):
+  scope = 'all_layers'
+
+
+_ALL_LAYERS = _AllLayers()
+
+
 def pack_all(layers):
   """Packs the operands of all `layers` with one launch on the current stream; their forward passes then skip
   the per-layer pack for this step."""
@@ -191,7 +201,7 @@ def pack_all(layers):
   plan = _PACK_PLANS.get(key)
   if plan is None:
     plan = _PACK_PLANS[key] = PackPlan()
-  plan.run(layers)
+  _timed('pack', _ALL_LAYERS, lambda: plan.run(layers))
   for l in layers:
     _PACKED_AHEAD.add(id(l))
 
@@ -277,10 +287,14 @@ class _MaskedConvFn(torch.autograd.Function):
       _SIDE_KEEP.append((x, dy16, patch_keep))     # no reuse of these blocks before the join
       mw.fresh = True
       mw.dense_grad.rigl_reduced = False           # rewritten: not yet summed over the replicas
+      if DP_HOOK is not None:
+        DP_HOOK.layer_done(layer, side)
     else:
       _timed('wgrad', layer, lambda: layer._wgrad(x, dy16, mw.dense_grad, accumulate=mw.fresh))
       mw.fresh = True
       mw.dense_grad.rigl_reduced = False
+      if DP_HOOK is not None:
+        DP_HOOK.layer_done(layer, None)
       if ctx.needs_input_grad[1] and not MASKED_GRAD_IN_OPTIMIZER:
         gw = layer.mask.apply_to(mw.dense_grad).view(layer.weight.shape)
     gb = None

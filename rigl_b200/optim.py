@@ -43,9 +43,12 @@ class FusedMomentumSGD(torch.optim.Optimizer):
       self._plan = C.c_void_p(None)
 
   # ---- masked layers: consume mask * dense_grad (* grad_scale) instead of weight.grad
-  def attach_masked_layers(self, layers, grad_scale=1.0):
+  def attach_masked_layers(self, layers, grad_scale=1.0, other_grad_scale=1.0):
+    """grad_scale multiplies the masked layers' dense gradients, other_grad_scale every other gradient
+    (1 / replicas when the buffers hold cross-replica SUMS)."""
     self._masked = {id(l.weight): l for l in layers}
     self._grad_scale = float(grad_scale)
+    self._other_scale = float(other_grad_scale)
     self._key = None
     return self
 
@@ -82,7 +85,7 @@ class FusedMomentumSGD(torch.optim.Optimizer):
       else:
         if p.grad is None:
           continue
-        grad, bits, scale = p.grad, None, 1.0
+        grad, bits, scale = p.grad, None, getattr(self, '_other_scale', 1.0)
       if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or grad.dtype != torch.float32 \
           or not grad.is_contiguous():
         raise ValueError('FusedMomentumSGD needs contiguous float32 CUDA parameters and gradients')

@@ -266,15 +266,19 @@ class TrainHarness(object):
                              use_tpu=data_parallel is not None).bind(model.registry)
     self.global_step = GlobalStep(0)
     self.dp = data_parallel
+    # RIGL_DP_OVERLAP=0: one blocking all-reduce after backward instead of the bucketed, overlapped exchange
+    self._dp_overlap = os.environ.get('RIGL_DP_OVERLAP', '1') != '0'
+    self._pack_ahead = on_cuda and os.environ.get('RIGL_PACK_AHEAD', '1') != '0'
     if self.dp is not None:
       self.dp.attach(model)
     if self.fused:
       # masked layers: the optimizer reads dense_grad (+ bitmap) directly; under data parallelism the buffers
       # hold the SUM over replicas, the weight update takes the mean (CrossShardOptimizer)
-      self.inner.attach_masked_layers(model.registry.layers(),
-                                      grad_scale=1.0 / self.dp.world if self.dp is not None else 1.0)
+      inv = 1.0 / self.dp.world if self.dp is not None else 1.0
+      self.inner.attach_masked_layers(model.registry.layers(), grad_scale=inv, other_grad_scale=inv)
       if self.dp is not None:
         self.dp.masked_grads_in_optimizer = True
+        self.dp.other_scale_in_optimizer = True
 
   def _apply_lr_schedule(self):
     if self.lr_schedule is None:
@@ -298,13 +302,10 @@ class TrainHarness(object):
     default from RIGL_WGRAD_OVERLAP (on unless '0')."""
     import os
     if overlap_wgrad is None:
-      # default: on for the single-GPU step (the validated configuration); with data parallelism the
-      # serial backward is kept until the fork has been measured together with the all-reduce
-      # (RIGL_WGRAD_OVERLAP=1 forces it on, =0 off)
-      env = os.environ.get('RIGL_WGRAD_OVERLAP')
-      overlap_wgrad = (env != '0') if (env is not None or self.dp is None) else False
+      # default on (RIGL_WGRAD_OVERLAP=0 keeps the serial backward); under data parallelism the bucketed
+      # all-reduces run behind the forked wgrad kernels on a third stream
+      overlap_wgrad = os.environ.get('RIGL_WGRAD_OVERLAP', '1') != '0' 
     self._overlap = bool(overlap_wgrad)
-    self._pack_ahead = self._overlap and os.environ.get('RIGL_PACK_AHEAD', '1') != '0'
     self._sx, self._sy = images.clone(), labels.clone()
     try:
       side = torch.cuda.Stream()
@@ -317,14 +318,15 @@ class TrainHarness(object):
       from . import _cabi
       self._g_fb = torch.cuda.CUDAGraph()
       before = _cabi.launch_count()
-      with torch.cuda.graph(self._g_fb):
+      # (thread-local capture mode: the NCCL watchdog thread keeps issuing CUDA calls while we capture)
+      with torch.cuda.graph(self._g_fb, capture_error_mode='thread_local'):
         self._sloss = self._forward_backward(self._sx, self._sy, set_to_none=False)
       self.graph_kernel_launches = _cabi.launch_count() - before     # rigl kernels inside one replay
       self.replayed_kernel_launches = 0
       self._g_opt = torch.cuda.CUDAGraph()
       if self.fused:
         self.inner.prepare()                   # slots / device lr / launch plan: allocated OUTSIDE the capture
-      with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool()):
+      with torch.cuda.graph(self._g_opt, pool=self._g_fb.pool(), capture_error_mode='thread_local'):
         self.inner.step()
       self.graphed = True
     except Exception as e:      # stay on the eager path, but say why
@@ -339,18 +341,25 @@ class TrainHarness(object):
     for mw in self.model.registry.get_masked_weights():
       mw.fresh = False
     self.inner.zero_grad(set_to_none=set_to_none)
-    if getattr(self, '_overlap', False) and getattr(self, '_pack_ahead', False):
+    if self._pack_ahead:
       # ONE launch packs the operands (mask * W -> bf16, both layouts) of every layer
       layers.pack_all(self.model.registry.layers())
     logits = self.model(images)
     loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
     layers.WGRAD_SIDE_STREAM = bool(getattr(self, '_overlap', False))
     layers.MASKED_GRAD_IN_OPTIMIZER = self.fused      # mask * dense_grad is formed inside the optimizer kernel
+    if self.dp is not None and self._dp_overlap:
+      self.dp.begin_backward()                        # bucketed all-reduces launched from inside backward
+      layers.DP_HOOK = self.dp
     try:
       loss.backward()
     finally:
       layers.WGRAD_SIDE_STREAM = False
       layers.MASKED_GRAD_IN_OPTIMIZER = False
+      layers.DP_HOOK = None
+      if self.dp is not None and self._dp_overlap:
+        side = [st for dev, st in layers._SIDE.items()]
+        self.dp.finish(self.model, producer_streams=side)       # head bucket + join of the communication stream
       layers.join_side_streams()                # (no-op when nothing was forked)
     return loss
 
@@ -360,7 +369,7 @@ class TrainHarness(object):
     self._sy.copy_(labels, non_blocking=True)
     self._g_fb.replay()
     self.replayed_kernel_launches += self.graph_kernel_launches
-    if self.dp is not None:
+    if self.dp is not None and not self._dp_overlap:
       self.dp.reduce_gradients(self.model)
     self.opt.collect_masked_grads()
     gs = self.global_step
@@ -377,20 +386,10 @@ class TrainHarness(object):
     if getattr(self, 'graphed', False):
       return self._graphed_step(images, labels)
     self._apply_lr_schedule()
-    from . import layers
-    for mw in self.model.registry.get_masked_weights():
-      mw.fresh = False
     # without DP the grads are re-created by autograd (no zero-fill, no accumulate pass);
     # with DP they are views of the flat all-reduce buffer and must persist
-    self.inner.zero_grad(set_to_none=self.dp is None)
-    logits = self.model(images)
-    loss = F.cross_entropy(logits.float(), labels, label_smoothing=self.label_smoothing)
-    layers.MASKED_GRAD_IN_OPTIMIZER = self.fused
-    try:
-      loss.backward()
-    finally:
-      layers.MASKED_GRAD_IN_OPTIMIZER = False
-    if self.dp is not None:
+    loss = self._forward_backward(images, labels, set_to_none=self.dp is None)
+    if self.dp is not None and not self._dp_overlap:
       self.dp.reduce_gradients(self.model)
     self.opt.collect_masked_grads()
     self.opt.apply_gradients(None, global_step=self.global_step)
