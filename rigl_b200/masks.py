@@ -163,9 +163,13 @@ class MaskUpdateEngine(object):
       self._ws = torch.empty(need, dtype=torch.uint8, device=layers[0]['weights'].device)
 
   def run(self, layers, drop_fraction, grow_mode=_cabi.GROW_ZEROS, grow_divisor=1.0, acc_scale=0.0,
-          reinit_when_same=False):
-    """One mask update of every layer; asynchronous on the current stream."""
-    self.prepare(layers)
+          reinit_when_same=False, plan_key=None):
+    """One mask update of every layer; asynchronous on the current stream.  plan_key: a caller-side key that
+    changes whenever any tensor of `layers` is reallocated; when it equals the key of the previous run the
+    per-layer validation / plan lookup is skipped (the host cost then does not scale with the layer count)."""
+    if plan_key is None or plan_key != getattr(self, '_caller_key', None) or not (self._plan and self._plan.value):
+      self.prepare(layers)
+      self._caller_key = plan_key
     _cabi.check(_cabi.lib().rigl_mask_update_run(
         self._plan, float(drop_fraction), int(grow_mode), float(grow_divisor), float(acc_scale),
         int(bool(reinit_when_same)), self._ws.data_ptr(), self._ws.numel(), _cabi.stream_ptr()),

@@ -114,6 +114,10 @@ def cross_replica_sum_(grads, enabled):
 class SparseSETOptimizerBase(object):
   """Wraps a torch optimizer; periodically drops by magnitude and regrows at random."""
 
+  # SET / Static redraw (or rebuild) their grow-score tensors at every update: the layer specs are rebuilt too.
+  # Optimizers whose specs only point at persistent buffers (RigL: the dense gradients) set this to True.
+  _specs_cacheable = False
+
   def __init__(self, optimizer, begin_step, end_step, frequency, drop_fraction=0.1,
                drop_fraction_anneal='constant', use_locking=False, grow_init='zeros',
                name='SparseSETOptimizer', use_stateless=True, stateless_seed_offset=0):
@@ -267,9 +271,24 @@ class SparseSETOptimizerBase(object):
     self._slot_names_cache = self.get_slot_names()
     try:
       noise = self._batched_noise([w for _, w in pairs], self.noise_std)
-      self._run_update([self._layer_spec(m, w, self.noise_std, noise=noise.get(w.name)) for m, w in pairs])
+      # The per-layer specs (54 dicts of tensor views for ResNet-50) only change when a buffer is reallocated or
+      # an optimizer slot appears: they are cached under a key of the storages involved, and the same key lets
+      # the engine skip re-validating its launch plan.
+      key = (self._grow_init, float(self.noise_std), tuple(self._slot_names_cache)) + tuple(
+          (id(m), w.data_ptr(), self._spec_cache_extra(w)) for m, w in pairs)
+      cacheable = self._specs_cacheable and (self._grow_init == 'zeros' or self._grow_init.startswith('grad_'))
+      cached = getattr(self, '_spec_cache', None)
+      if not cacheable or cached is None or cached[0] != key:
+        specs = [self._layer_spec(m, w, self.noise_std, noise=noise.get(w.name)) for m, w in pairs]
+        self._spec_cache = (key, specs)
+      self._run_update(self._spec_cache[1], plan_key=key if cacheable else None)
     finally:
       self._slot_names_cache = None
+
+  def _spec_cache_extra(self, weights):
+    """Whatever else a cached layer spec points at (subclasses: the dense-gradient / EMA buffer)."""
+    st = self._optimizer.state.get(weights) if hasattr(self._optimizer, 'state') else None
+    return tuple(v.data_ptr() for v in st.values() if torch.is_tensor(v) and v.dim() > 0) if st else ()
 
   def _batched_noise(self, weights, noise_std):
     if not noise_std:
@@ -359,13 +378,15 @@ class SparseSETOptimizerBase(object):
                 flags=_cabi.LAYER_GROW_SCORE_SIGNED if signed_grow else 0,
                 grad=self._grad_for(weights) if signed_grow else None)
 
-  def _run_update(self, specs):
-    modes = {(s['grow_mode'], s['grow_divisor'], s['reinit_when_same']) for s in specs}
-    if len(modes) != 1:
-      raise ValueError('all layers of one update must share grow_init / reinit mode')
-    mode, div, reinit = modes.pop()
+  def _run_update(self, specs, plan_key=None):
+    first = specs[0]
+    mode, div, reinit = first['grow_mode'], first['grow_divisor'], first['reinit_when_same']
+    if plan_key is None or plan_key != getattr(self, '_checked_modes_key', None):
+      if any((s['grow_mode'], s['grow_divisor'], s['reinit_when_same']) != (mode, div, reinit) for s in specs):
+        raise ValueError('all layers of one update must share grow_init / reinit mode')
+      self._checked_modes_key = plan_key
     self._engine.run(specs, np.float32(self.drop_fraction), grow_mode=mode, grow_divisor=div,
-                     acc_scale=self._acc_scale(), reinit_when_same=reinit)
+                     acc_scale=self._acc_scale(), reinit_when_same=reinit, plan_key=plan_key)
 
   def generic_mask_update(self, mask, weights, noise_std=1e-5):
     """Drop/grow of ONE layer with the optimizer's scores (uses self.drop_fraction)."""
@@ -442,6 +463,8 @@ class SparseSETOptimizerBase(object):
 class SparseRigLOptimizerBase(SparseSETOptimizerBase):
   """Grows where the DENSE gradient magnitude is largest (Evci et al., RigL)."""
 
+  _specs_cacheable = True
+
   def __init__(self, optimizer, begin_step, end_step, frequency, drop_fraction=0.1,
                drop_fraction_anneal='constant', use_locking=False, grow_init='zeros',
                initial_acc_scale=0., use_tpu=False, name='SparseRigLOptimizer',
@@ -487,6 +510,10 @@ class SparseRigLOptimizerBase(SparseSETOptimizerBase):
 
   def _score_grow_for(self, mask, weights):
     return self._weight2masked_grads[weights.name]       # |.| is taken in the kernel
+
+  def _spec_cache_extra(self, weights):
+    g = self._weight2masked_grads.get(weights.name)
+    return super(SparseRigLOptimizerBase, self)._spec_cache_extra(weights) + ((g.data_ptr(),) if g is not None else ())
 
   def _grad_for(self, weights):
     g = self._weight2masked_grads.get(weights.name)

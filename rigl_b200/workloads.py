@@ -358,7 +358,9 @@ class TrainHarness(object):
       layers.MASKED_GRAD_IN_OPTIMIZER = False
       layers.DP_HOOK = None
       if self.dp is not None and self._dp_overlap:
-        side = [st for dev, st in layers._SIDE.items()]
+        # (only a side stream that was forked in THIS backward may be waited on: under capture a wait on a
+        #  stream outside the capture is an error)
+        side = list(layers._SIDE.values()) if getattr(self, '_overlap', False) else []
         self.dp.finish(self.model, producer_streams=side)       # head bucket + join of the communication stream
       layers.join_side_streams()                # (no-op when nothing was forked)
     return loss
