@@ -89,6 +89,8 @@ typedef struct {
   int64_t n;                 /* elements, 1 <= n < 2^31                          */
   int32_t n_prune_override;  /* >= 0: use this n_prune; -1: int32(float32(n_ones)*drop_fraction) */
   int32_t flags;             /* RIGL_LAYER_* bits */
+  uint32_t noise_key;        /* per-layer key of the in-kernel drop-score noise (rigl_mask_update_run_noise) */
+  uint32_t reserved;
   const float* grad;         /* [n] gradient read by RIGL_GROW_GRAD_SCALE / _SIGN and by the slot reset
                                 (slot <- grad * acc_scale), base.py:540-564; NULL: score_grow is the gradient
                                 (the RigL / Momentum callers, whose grow score IS the dense gradient) */
@@ -131,6 +133,17 @@ RIGL_API size_t rigl_mask_plan_workspace_bytes(const rigl_mask_plan* plan);
 RIGL_API int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
                          float grow_divisor, float acc_scale, int reinit_when_same,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the drop-score noise of generic_mask_update (noise_std, base.py:260-274, 523-538) drawn IN-KERNEL
+ * for every layer whose `noise` pointer is NULL (and that has no explicit score_drop): element i of a layer gets
+ * noise_std * N(0,1) from a counter-based generator keyed by (noise_seed, layer noise_key, i) -- no noise tensor
+ * is written or read.  noise_std = 0 behaves like rigl_mask_update_run. */
+RIGL_API int rigl_mask_update_run_noise(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
+                         float grow_divisor, float acc_scale, int reinit_when_same, float noise_std,
+                         uint64_t noise_seed, void* workspace, size_t workspace_bytes, void* stream);
+/* out[i] <- exactly the noise rigl_mask_update_run_noise adds to element i of a layer with this key
+ * (tests and the CPU oracle consume it; the product path never materialises it). */
+RIGL_API int rigl_mask_noise_fill(float* out, int64_t n, uint32_t layer_noise_key, float noise_std,
+                         uint64_t noise_seed, void* stream);
 /* Copies 8 int32 per layer {n_ones, n_prune, n_keep, drop_candidates, grow_candidates,
  * drop_bucket, grow_bucket, 0} to host (synchronises the stream). */
 RIGL_API int rigl_mask_plan_read_stats(const rigl_mask_plan* plan, const void* workspace,

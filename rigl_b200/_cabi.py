@@ -19,7 +19,8 @@ class RiglError(RuntimeError):
 class LayerDesc(C.Structure):
   _fields_ = [('weights', C.c_void_p), ('score_grow', C.c_void_p), ('mask_bits', C.c_void_p),
               ('noise', C.c_void_p), ('slots', C.c_void_p * 2), ('grow_values', C.c_void_p), ('score_drop', C.c_void_p),
-              ('n', C.c_int64), ('n_prune_override', C.c_int32), ('flags', C.c_int32), ('grad', C.c_void_p)]
+              ('n', C.c_int64), ('n_prune_override', C.c_int32), ('flags', C.c_int32), ('noise_key', C.c_uint32),
+              ('reserved', C.c_uint32), ('grad', C.c_void_p)]
 
 
 class PackDesc(C.Structure):
@@ -57,6 +58,8 @@ SIGNATURES = {
     'rigl_mask_plan_destroy': (C.c_int, [_vp]),
     'rigl_mask_plan_workspace_bytes': (_sz, [_vp]),
     'rigl_mask_update_run': (C.c_int, [_vp, _f32, _i32, _f32, _f32, _i32, _vp, _sz, _vp]),
+    'rigl_mask_update_run_noise': (C.c_int, [_vp, _f32, _i32, _f32, _f32, _i32, _f32, C.c_uint64, _vp, _sz, _vp]),
+    'rigl_mask_noise_fill': (C.c_int, [_vp, _i64, C.c_uint32, _f32, C.c_uint64, _vp]),
     'rigl_mask_plan_read_stats': (C.c_int, [_vp, _vp, C.POINTER(C.c_int32), _vp]),
     'rigl_packed_weights_bytes': (_sz, [_i32, _i32, _i32]),
     'rigl_pack_masked_weights': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -63,6 +63,7 @@ struct LayerDev {
   const float* sdrop;
   const float* grad;      // gradient for grad_scale / grad_sign init and the slot reset (null: score_grow is it)
   uint32_t flags;         // RIGL_LAYER_* bits
+  uint32_t noise_key;     // per-layer key of the in-kernel drop-score noise
   uint32_t n;
   int32_t n_prune_override;
   uint64_t off_mask1;   // byte offsets into the workspace
@@ -85,7 +86,51 @@ struct RunParams {
   float grow_divisor;
   float acc_scale;
   int reinit_when_same;
+  float noise_std;            // > 0: layers without a noise tensor draw N(0, noise_std) in-kernel
+  uint32_t seed_lo, seed_hi;  // run key of that draw (seed offset + hash | global step)
 };
+
+// Counter-based N(0,1) noise for the drop scores (generic_mask_update's `noise_std`, base.py:260-274, 523-538):
+// element i of a layer takes one half of a Box-Muller pair from Philox2x32-10(counter = (i >> 1, seed_hi),
+// key = layer_key ^ seed_lo).  No tensor is written or read: the two scans that need the noise recompute it.
+// Every fp op is an explicit round-to-nearest intrinsic or a MUFU approximation, so the value of element i is the
+// same in every kernel (and in rigl_mask_noise_fill, which materialises it for the tests / the oracle).
+__device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key, uint32_t& o0, uint32_t& o1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+    c0 = hi ^ key ^ c1;
+    c1 = lo;
+    key += 0x9E3779B9u;
+  }
+  o0 = c0; o1 = c1;
+}
+
+__device__ __forceinline__ float2 normal_pair(uint32_t pair_idx, uint32_t layer_key, uint32_t seed_lo, uint32_t seed_hi) {
+  uint32_t x0, x1;
+  philox2x32_10(pair_idx, seed_hi, layer_key ^ seed_lo, x0, x1);
+  const float u1 = __fmul_rn((float)((x0 >> 8) + 1u), 5.9604644775390625e-08f);      // (0, 1]
+  const float u2 = __fmul_rn((float)(x1 >> 8), 5.9604644775390625e-08f);             // [0, 1)
+  const float r = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u1)));
+  const float th = __fmul_rn(6.2831853071795864769f, u2);
+  return make_float2(__fmul_rn(r, __cosf(th)), __fmul_rn(r, __sinf(th)));
+}
+
+// noise of elements e0 .. e0+3 (e0 a multiple of 4)
+__device__ __forceinline__ float4 noise4(uint32_t e0, uint32_t layer_key, const RunParams& prm) {
+  const float2 a = normal_pair(e0 >> 1, layer_key, prm.seed_lo, prm.seed_hi);
+  const float2 b = normal_pair((e0 >> 1) + 1u, layer_key, prm.seed_lo, prm.seed_hi);
+  return make_float4(__fmul_rn(a.x, prm.noise_std), __fmul_rn(a.y, prm.noise_std), __fmul_rn(b.x, prm.noise_std),
+                     __fmul_rn(b.y, prm.noise_std));
+}
+
+__global__ void k_noise_fill(float* __restrict__ out, uint32_t n, uint32_t layer_key, RunParams prm) {
+  const uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (e0 >= n) return;
+  const float4 v = noise4(e0, layer_key, prm);
+  const float vs[4] = {v.x, v.y, v.z, v.w};
+  for (int c = 0; c < 4 && e0 + c < n; ++c) out[e0 + c] = vs[c];
+}
 
 __device__ __forceinline__ float4 load4_guard(const float* __restrict__ p, uint32_t e0, uint32_t n) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -134,7 +179,7 @@ __device__ __forceinline__ void flush_hist(const uint32_t* sh, uint32_t* gh) {
 // A: histogram of drop keys
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads, 4)
-k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws) {
+k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
@@ -143,7 +188,8 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool explicit_score = L.sdrop != nullptr;
-  const bool has_noise = L.noise != nullptr && !explicit_score;
+  const bool gen_noise = L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
+  const bool has_noise = (L.noise != nullptr && !explicit_score) || gen_noise;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
   const bool all_active = (L.flags & RIGL_LAYER_ALL_ACTIVE) != 0;     // rank every position (mask treated as ones)
@@ -164,7 +210,8 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       nv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (act[u]) {
         wv[u] = load4_guard(wsrc, e0s[u], n);
-        if (has_noise) nv[u] = load4_guard(L.noise, e0s[u], n);
+        if (gen_noise) nv[u] = noise4(e0s[u], L.noise_key, prm);
+        else if (has_noise) nv[u] = load4_guard(L.noise, e0s[u], n);
         mw[u] = __ldg(L.mask + (base >> 5) + (lane >> 3));
       }
     }
@@ -300,7 +347,7 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
 // C: classify against the drop threshold bin, build mask1, grow histogram
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads, 4)
-k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws) {
+k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
@@ -313,7 +360,8 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const uint32_t bucket = (uint32_t)st->drop_bucket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool explicit_score = L.sdrop != nullptr;
-  const bool has_noise = L.noise != nullptr && !explicit_score;
+  const bool gen_noise = L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
+  const bool has_noise = (L.noise != nullptr && !explicit_score) || gen_noise;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
   const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
@@ -335,7 +383,8 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
         const uint32_t e0 = bases[u] + 4 * lane;
         wv[u] = load4_guard(wsrc, e0, n);
         gv[u] = load4_guard(L.g, e0, n);
-        if (has_noise) nv[u] = load4_guard(L.noise, e0, n);
+        if (gen_noise) nv[u] = noise4(e0, L.noise_key, prm);
+        else if (has_noise) nv[u] = load4_guard(L.noise, e0, n);
         mw[u] = __ldg(L.mask + (bases[u] >> 5) + (lane >> 3));
       }
     }
@@ -666,7 +715,7 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
     LayerDev& L = host[l];
     L.w = d.weights; L.g = d.score_grow; L.mask = d.mask_bits; L.noise = d.noise;
     L.slot0 = d.slots[0]; L.slot1 = d.slots[1]; L.grow = d.grow_values; L.sdrop = d.score_drop;
-    L.grad = d.grad; L.flags = (uint32_t)d.flags;
+    L.grad = d.grad; L.flags = (uint32_t)d.flags; L.noise_key = d.noise_key;
     L.n = (uint32_t)d.n; L.n_prune_override = d.n_prune_override;
     L.off_state = state_off + sizeof(LayerState) * (size_t)l;
     L.off_hist_drop = hist_drop_off + (size_t)l * kBins * 4;
@@ -711,26 +760,25 @@ extern "C" size_t rigl_mask_plan_workspace_bytes(const rigl_mask_plan* plan) {
   return plan ? plan->ws_bytes : 0;
 }
 
-extern "C" int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
-                                    float grow_divisor, float acc_scale, int reinit_when_same,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
+static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm, void* workspace, size_t workspace_bytes,
+                              void* stream_) {
   RIGL_REQUIRE(plan && workspace, "rigl_mask_update_run: null plan/workspace");
   if (workspace_bytes < plan->ws_bytes) {
     set_error("rigl_mask_update_run: workspace %zu < required %zu", workspace_bytes, plan->ws_bytes);
     return RIGL_ERR_WORKSPACE;
   }
   RIGL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256B aligned");
-  RIGL_REQUIRE(grow_mode >= RIGL_GROW_ZEROS && grow_mode <= RIGL_GROW_GRAD_SIGN, "bad grow_mode %d", grow_mode);
-  RIGL_REQUIRE(drop_fraction >= 0.f && drop_fraction <= 1.f, "drop_fraction %f outside [0,1]", drop_fraction);
+  RIGL_REQUIRE(prm.grow_mode >= RIGL_GROW_ZEROS && prm.grow_mode <= RIGL_GROW_GRAD_SIGN, "bad grow_mode %d", prm.grow_mode);
+  RIGL_REQUIRE(prm.drop_fraction >= 0.f && prm.drop_fraction <= 1.f, "drop_fraction %f outside [0,1]", prm.drop_fraction);
+  RIGL_REQUIRE(prm.noise_std >= 0.f, "noise_std must be >= 0");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same};
   RIGL_CUDA(cudaMemsetAsync(ws, 0, plan->zero_bytes, stream));
-  k_hist_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws);
+  k_hist_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
   RIGL_LAUNCH_CHECK("k_hist_drop");
   k_pick_drop<<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_pick_drop");
-  k_scan_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws);
+  k_scan_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
   RIGL_LAUNCH_CHECK("k_scan_drop");
   k_resolve<false><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_resolve<drop>");
@@ -738,6 +786,32 @@ extern "C" int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, i
   RIGL_LAUNCH_CHECK("k_scan_grow");
   k_resolve<true><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_resolve<grow>");
+  return RIGL_OK;
+}
+
+extern "C" int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
+                                    float grow_divisor, float acc_scale, int reinit_when_same,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, 0.f, 0u, 0u};
+  return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int rigl_mask_update_run_noise(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
+                                          float grow_divisor, float acc_scale, int reinit_when_same,
+                                          float noise_std, uint64_t noise_seed, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std,
+                (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32)};
+  return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int rigl_mask_noise_fill(float* out, int64_t n, uint32_t layer_noise_key, float noise_std,
+                                    uint64_t noise_seed, void* stream_) {
+  RIGL_REQUIRE(out && n >= 1 && n < (1ll << 31) && noise_std >= 0.f, "rigl_mask_noise_fill: bad arguments");
+  RunParams prm{0.f, 0, 1.f, 0.f, 0, noise_std, (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32)};
+  const unsigned blocks = (unsigned)((n + 1023) / 1024);
+  k_noise_fill<<<blocks, 256, 0, (cudaStream_t)stream_>>>(out, (uint32_t)n, layer_noise_key, prm);
+  RIGL_LAUNCH_CHECK("k_noise_fill");
   return RIGL_OK;
 }
 

@@ -91,8 +91,9 @@ class MaskUpdateEngine(object):
   Each layer is a dict with tensors (float32, contiguous, same numel):
     weights, score_grow, mask (MaskVariable), and optional noise, slots (list of
     up to 2 tensors), grow_values, score_drop, n_prune (int override), grad (the gradient the
-    grad_* grow inits and the slot reset read when it is not score_grow itself) and flags
-    (_cabi.LAYER_GROW_SCORE_SIGNED: rank score_grow verbatim instead of |score_grow|).
+    grad_* grow inits and the slot reset read when it is not score_grow itself), flags
+    (_cabi.LAYER_GROW_SCORE_SIGNED: rank score_grow verbatim instead of |score_grow|; LAYER_DROP_ONLY;
+    LAYER_ALL_ACTIVE) and noise_key (per-layer key of the in-kernel noise, see `run(noise_std=...)`).
   The C plan captures raw pointers, so it is rebuilt whenever any pointer changes.
   """
 
@@ -119,7 +120,7 @@ class MaskUpdateEngine(object):
     return (ly['weights'].data_ptr(), ly['score_grow'].data_ptr(), ly['mask'].bits.data_ptr(),
             _ptr(ly.get('noise')), tuple(s.data_ptr() for s in slots), _ptr(ly.get('grow_values')),
             _ptr(ly.get('score_drop')), int(ly['mask'].size), int(ly.get('n_prune', -1)),
-            _ptr(ly.get('grad')), int(ly.get('flags', 0)))
+            _ptr(ly.get('grad')), int(ly.get('flags', 0)), int(ly.get('noise_key', 0)))
 
   def prepare(self, layers):
     key = tuple(self._layer_key(ly) for ly in layers)
@@ -150,6 +151,7 @@ class MaskUpdateEngine(object):
       d.score_drop = _ptr(ly.get('score_drop'))
       d.grad = _ptr(ly.get('grad'))
       d.flags = int(ly.get('flags', 0))
+      d.noise_key = int(ly.get('noise_key', 0)) & 0xffffffff
       d.n = n
       d.n_prune_override = int(ly.get('n_prune', -1))
     plan = C.c_void_p(None)
@@ -163,13 +165,21 @@ class MaskUpdateEngine(object):
       self._ws = torch.empty(need, dtype=torch.uint8, device=layers[0]['weights'].device)
 
   def run(self, layers, drop_fraction, grow_mode=_cabi.GROW_ZEROS, grow_divisor=1.0, acc_scale=0.0,
-          reinit_when_same=False, plan_key=None):
+          reinit_when_same=False, plan_key=None, noise_std=0.0, noise_seed=0):
     """One mask update of every layer; asynchronous on the current stream.  plan_key: a caller-side key that
     changes whenever any tensor of `layers` is reallocated; when it equals the key of the previous run the
     per-layer validation / plan lookup is skipped (the host cost then does not scale with the layer count)."""
     if plan_key is None or plan_key != getattr(self, '_caller_key', None) or not (self._plan and self._plan.value):
       self.prepare(layers)
       self._caller_key = plan_key
+    if noise_std:
+      # drop-score noise drawn in-kernel for the layers without a `noise` tensor (keyed by noise_seed and each
+      # layer's `noise_key`; rigl_mask_noise_fill reproduces it)
+      _cabi.check(_cabi.lib().rigl_mask_update_run_noise(
+          self._plan, float(drop_fraction), int(grow_mode), float(grow_divisor), float(acc_scale),
+          int(bool(reinit_when_same)), float(noise_std), int(noise_seed) & 0xffffffffffffffff, self._ws.data_ptr(),
+          self._ws.numel(), _cabi.stream_ptr()), 'rigl_mask_update_run_noise')
+      return
     _cabi.check(_cabi.lib().rigl_mask_update_run(
         self._plan, float(drop_fraction), int(grow_mode), float(grow_divisor), float(acc_scale),
         int(bool(reinit_when_same)), self._ws.data_ptr(), self._ws.numel(), _cabi.stream_ptr()),
@@ -185,3 +195,13 @@ class MaskUpdateEngine(object):
   @property
   def workspace_bytes(self):
     return 0 if self._ws is None else self._ws.numel()
+
+
+def noise_fill(n, noise_key, noise_std, noise_seed, device):
+  """The noise tensor `MaskUpdateEngine.run(noise_std=..., noise_seed=...)` adds in-kernel to the drop scores of a
+  layer with `noise_key` (float32 [n]); for tests / the oracle -- the product path never materialises it."""
+  out = torch.empty(int(n), dtype=torch.float32, device=device)
+  _cabi.check(_cabi.lib().rigl_mask_noise_fill(out.data_ptr(), int(n), int(noise_key) & 0xffffffff, float(noise_std),
+                                               int(noise_seed) & 0xffffffffffffffff, _cabi.stream_ptr()),
+              'rigl_mask_noise_fill')
+  return out

@@ -141,6 +141,12 @@ class SparseSETOptimizerBase(object):
     self.drop_fraction = np.float32(0.)
     self.noise_std = 1e-5                   # default of generic_mask_update (base.py:260,523)
     self.last_update_was_mask_update = False
+    # the drop-score noise is drawn inside the select kernels from a counter-based generator keyed like
+    # `_generator` (seed offset + crc32('drop'), global step) and per layer by crc32(name + 'drop'); no noise
+    # tensor exists.  RIGL_INKERNEL_NOISE=0 (or use_stateless=False): a torch.Generator draw into a flat buffer.
+    import os
+    self._inkernel_noise = bool(use_stateless) and os.environ.get('RIGL_INKERNEL_NOISE', '1') != '0'
+    self._last_noise = None                 # (noise_std, seed) of the last in-kernel draw
 
   # ---- getter triple: supplied by a mixin (sparse_optimizers.PruningGetterTorchMixin)
   def get_weights(self):
@@ -270,7 +276,7 @@ class SparseSETOptimizerBase(object):
       return
     self._slot_names_cache = self.get_slot_names()
     try:
-      noise = self._batched_noise([w for _, w in pairs], self.noise_std)
+      noise = {} if self._inkernel_noise else self._batched_noise([w for _, w in pairs], self.noise_std)
       # The per-layer specs (54 dicts of tensor views for ResNet-50) only change when a buffer is reallocated or
       # an optimizer slot appears: they are cached under a key of the storages involved, and the same key lets
       # the engine skip re-validating its launch plan.
@@ -281,7 +287,7 @@ class SparseSETOptimizerBase(object):
       if not cacheable or cached is None or cached[0] != key:
         specs = [self._layer_spec(m, w, self.noise_std, noise=noise.get(w.name)) for m, w in pairs]
         self._spec_cache = (key, specs)
-      self._run_update(self._spec_cache[1], plan_key=key if cacheable else None)
+      self._run_update(self._spec_cache[1], plan_key=key if cacheable else None, noise_std=self.noise_std)
     finally:
       self._slot_names_cache = None
 
@@ -368,29 +374,47 @@ class SparseSETOptimizerBase(object):
     mode, div, grow_values = self._grow_spec(weights, self._grow_init)
     if score_grow is None:
       score_grow = self._score_grow_for(mask, weights)
-    if noise is None and score_drop is None:
+    if noise is None and score_drop is None and not self._inkernel_noise:
       noise = self._noise_for(weights, noise_std)
     return dict(mask=mask, weights=weights.data.view(-1), score_grow=score_grow.contiguous().view(-1),
                 noise=None if score_drop is not None else noise,
                 score_drop=None if score_drop is None else score_drop.contiguous().view(-1),
                 slots=self._slots_of(weights), grow_values=grow_values, grow_mode=mode,
                 grow_divisor=div, reinit_when_same=reinit_when_same,
+                noise_key=stable_hash(weights.name + 'drop'),
                 flags=_cabi.LAYER_GROW_SCORE_SIGNED if signed_grow else 0,
                 grad=self._grad_for(weights) if signed_grow else None)
 
-  def _run_update(self, specs, plan_key=None):
+  def _noise_seed(self):
+    gs = int(self._global_step) if self._global_step is not None else 0
+    return (((self._stateless_seed_offset + stable_hash('drop')) & 0x7fffffff) << 32) | (gs & 0xffffffff)
+
+  def last_update_noise(self, weights):
+    """The noise the last update added in-kernel to the drop scores of `weights` (float32, flat), re-materialised
+    for inspection / the CPU oracle; None when that update drew none."""
+    if self._last_noise is None or not self._last_noise[0]:
+      return None
+    from .masks import noise_fill
+    std, seed = self._last_noise
+    return noise_fill(weights.numel(), stable_hash(weights.name + 'drop'), std, seed, weights.device)
+
+  def _run_update(self, specs, plan_key=None, noise_std=0.0):
     first = specs[0]
     mode, div, reinit = first['grow_mode'], first['grow_divisor'], first['reinit_when_same']
     if plan_key is None or plan_key != getattr(self, '_checked_modes_key', None):
       if any((s['grow_mode'], s['grow_divisor'], s['reinit_when_same']) != (mode, div, reinit) for s in specs):
         raise ValueError('all layers of one update must share grow_init / reinit mode')
       self._checked_modes_key = plan_key
+    std = float(noise_std) if (self._inkernel_noise and noise_std) else 0.0
+    seed = self._noise_seed() if std else 0
+    self._last_noise = (std, seed)
     self._engine.run(specs, np.float32(self.drop_fraction), grow_mode=mode, grow_divisor=div,
-                     acc_scale=self._acc_scale(), reinit_when_same=reinit, plan_key=plan_key)
+                     acc_scale=self._acc_scale(), reinit_when_same=reinit, plan_key=plan_key,
+                     noise_std=std, noise_seed=seed)
 
   def generic_mask_update(self, mask, weights, noise_std=1e-5):
     """Drop/grow of ONE layer with the optimizer's scores (uses self.drop_fraction)."""
-    self._run_update([self._layer_spec(mask, weights, noise_std)])
+    self._run_update([self._layer_spec(mask, weights, noise_std)], noise_std=noise_std)
     return mask
 
   def _get_update_op(self, score_drop, score_grow, mask, weights, reinit_when_same=False):

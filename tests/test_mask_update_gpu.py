@@ -327,3 +327,38 @@ def test_explicit_signed_grow_scores_with_separate_gradient(mode):
   MaskUpdateEngine().run([dict(mask=mv2, weights=_t(w).view(-1), score_grow=_t(sg).view(-1),
                                score_drop=_t(sd).view(-1))], np.float32(0.4))
   assert not np.array_equal(mv2.numpy(), want['mask'])
+
+
+def test_in_kernel_noise_equals_materialised_noise():
+  """rigl_mask_update_run_noise draws the drop-score noise inside the two scans that need it (no noise tensor);
+  rigl_mask_noise_fill materialises the same values: an update with the in-kernel draw is bit-identical to the
+  oracle (and to the tensor-noise path) fed that tensor.  Also checks the draw is a plausible N(0, std)."""
+  from rigl_b200.masks import noise_fill
+  rng = np.random.RandomState(21)
+  shapes = [(3, 3, 64, 64), (784, 300), (70001,), (5,)]
+  std, seed = 1e-3, (1234567 << 32) | 4100
+  layers = [_layer(rng, sh, 0.8, slots=1) for sh in shapes]
+  for ly in layers:
+    ly['w'] = (ly['w'] * np.float32(0.02)).astype(np.float32)         # |w| comparable to the noise: it decides ranks
+  keys = [101, 0xdeadbeef, 7, 0]
+  noises = [noise_fill(int(np.prod(sh)), k, std, seed, DEV).cpu().numpy().reshape(sh) for sh, k in zip(shapes, keys)]
+  big = noises[2].astype(np.float64)
+  assert abs(big.mean()) < 5 * std / np.sqrt(big.size) and abs(big.std() - std) < 0.02 * std
+  assert np.unique(big).size > 0.99 * big.size
+  assert not np.array_equal(noises[0].ravel()[:5], noises[1].ravel()[:5])           # layer key matters
+  other = noise_fill(5, 0, std, seed + 1, DEV).cpu().numpy()
+  assert not np.array_equal(other, noises[3].ravel())                               # seed (global step) matters
+  specs = []
+  for i, (ly, k) in enumerate(zip(layers, keys)):
+    mv = MaskVariable('n%d' % i, ly['mask'].shape, DEV).assign(ly['mask'])
+    specs.append(dict(mask=mv, weights=_t(ly['w']).view(-1), score_grow=_t(ly['g']).view(-1),
+                      slots=[_t(ly['slots'][0]).view(-1)], noise_key=k))
+  MaskUpdateEngine().run(specs, np.float32(0.3), noise_std=std, noise_seed=seed)
+  for ly, spec, nz in zip(layers, specs, noises):
+    want = orc.rigl_mask_update(ly['mask'], ly['w'], ly['g'], np.float32(0.3), noise=nz, slots=ly['slots'])
+    assert np.array_equal(spec['mask'].numpy(), want['mask'])
+    assert spec['weights'].cpu().numpy().reshape(ly['w'].shape).tobytes() == want['weights'].tobytes()
+    assert spec['slots'][0].cpu().numpy().reshape(ly['w'].shape).tobytes() == want['slots'][0].tobytes()
+    # and the noise really changed the outcome relative to a noiseless update
+  quiet = orc.rigl_mask_update(layers[1]['mask'], layers[1]['w'], layers[1]['g'], np.float32(0.3))
+  assert not np.array_equal(quiet['mask'], specs[1]['mask'].numpy())

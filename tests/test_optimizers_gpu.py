@@ -190,7 +190,7 @@ def test_rigl_update_through_public_api_matches_oracle():
   frac = orc.get_drop_fraction('cosine', 0.3, 100, 0, 50000, True)
   assert np.float32(so.drop_fraction) == frac
   for l, s in zip(layers, snap):
-    noise = so._noise_bufs[l.weight.name].cpu().numpy().reshape(s['w'].shape)
+    noise = so.last_update_noise(l.weight).cpu().numpy().reshape(s['w'].shape)       # drawn in-kernel, re-materialised
     want = orc.rigl_mask_update(s['mask'], s['w'], s['g'], frac, noise=noise, initial_acc_scale=0.25,
                                 slots=[s['mom']])
     assert np.array_equal(l.mask.numpy(), want['mask'])

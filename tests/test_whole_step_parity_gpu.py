@@ -127,7 +127,7 @@ def _check_update_steps(model, harness, images, labels, n_steps, expect_updates)
     frac = np.float32(harness.opt.drop_fraction)
     for l, (m0, w0, mom0) in zip(layers, before):
       dense = l.masked_weights.dense_grad.view(l.weight.shape).cpu().numpy()
-      noise = harness.opt._noise_bufs[l.weight.name].view(l.weight.shape).cpu().numpy()
+      noise = harness.opt.last_update_noise(l.weight).view(l.weight.shape).cpu().numpy()   # what the kernels drew
       want = orc.rigl_mask_update(m0, w0, dense, frac, noise=noise, slots=[] if mom0 is None else [mom0])
       assert np.array_equal(l.mask.numpy(), want['mask']), (gs, l.scope)
       assert l.weight.detach().cpu().numpy().tobytes() == want['weights'].tobytes(), (gs, l.scope)
