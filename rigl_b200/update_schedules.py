@@ -87,3 +87,44 @@ class ScaledLRUpdateSchedule(UpdateSchedule):
   def get_drop_fraction(self, step):
     current_lr = self._get_lr(step)
     return F32(F32(self.init_drop_fraction / F32(self._initial_lr)) * F32(current_lr))
+
+
+class MaskUpdaterAdapter(object):
+  """The `mask_updater` the schedules drive, over a rigl_b200 sparse optimizer and its batched CUDA mask update:
+  the counterpart of rigl_tf2/mask_updaters.py:33-160 (`MaskUpdater.update_masks` / `prune_masks`), whose per-layer
+  `generic_mask_update` is the same drop/grow as sparse_optimizers_base._get_update_op.
+
+    update_masks(f): drop the fraction f of every layer's active weights by |mask * w| (no noise, like the TF2
+                     updaters' default noise_std = 0) and grow as many by the optimizer's grow score
+                     (SET: uniform draw, RigL: |dense gradient|); grown weights <- 0, their optimizer slots <- 0.
+    prune_masks(f):  drop only (score_grow = None in the reference): every layer keeps its top n_ones - int(n_ones*f).
+  """
+
+  def __init__(self, sparse_optimizer):
+    self._opt = sparse_optimizer
+    self.val_x = self.val_y = None
+
+  def update_masks(self, drop_fraction):
+    opt = self._opt
+    if hasattr(opt, 'collect_masked_grads'):
+      opt.collect_masked_grads()
+    old_std, opt.noise_std = opt.noise_std, 0.
+    try:
+      opt.drop_fraction = F32(drop_fraction)
+      opt.mask_update_op()
+    finally:
+      opt.noise_std = old_std
+
+  def prune_masks(self, prune_fraction):
+    from . import _cabi
+    opt = self._opt
+    opt.drop_fraction = F32(prune_fraction)
+    specs = []
+    for m, w in zip(opt.get_masks(), opt.get_weights()):
+      flat = w.data.view(-1)
+      specs.append(dict(mask=m, weights=flat, score_grow=flat, flags=_cabi.LAYER_DROP_ONLY))
+    if specs:
+      opt._engine.run(specs, F32(prune_fraction))
+
+  def set_validation_data(self, val_x, val_y):
+    self.val_x, self.val_y = val_x, val_y

@@ -356,3 +356,49 @@ def test_dnw_trains_with_dense_gradient_and_tracks_topk():
     assert np.abs((w1 - w0)[m0 == 0]).max() > 0                  # masked-out weights received the dense gradient
     assert np.array_equal(layer.mask.numpy(), orc.dnw_mask(w1, 0.75))
   assert gs.value == 3
+
+
+def test_tf2_style_schedule_drives_the_cuda_mask_update():
+  """update_schedules.CosineUpdateSchedule (rigl_tf2/mask_updaters.py:251-344) over MaskUpdaterAdapter: at every
+  update step the masks / weights equal the oracle's restatement of the TF2 generic_mask_update (:99-154) with the
+  schedule's float32 drop fraction; `prune` drops without growing."""
+  from rigl_b200 import update_schedules as us
+  pruning.reset_default_registry()
+  rng = np.random.RandomState(8)
+  torch.manual_seed(8)
+  layer = SparseLinear(60, 50, use_bias=False, name='layer1', device=DEV, out_dtype=torch.float32)
+  layer.mask.assign(orc.get_mask_random_numpy((60, 50), 0.8, rng))
+  inner = torch.optim.SGD(layer.parameters(), lr=0.05, momentum=0.9)
+  so = sparse_optimizers.SparseRigLOptimizer(inner, 10 ** 9, 10 ** 9 + 1, 1, drop_fraction=0.3)   # own schedule never fires
+  sched = us.CosineUpdateSchedule(us.MaskUpdaterAdapter(so), 0.3, update_freq=4, last_update_step=40)
+  gs = GlobalStep(0)
+  x, t = torch.randn(32, 60, device=DEV), torch.randn(32, 50, device=DEV)
+  n_updates = 0
+  for step in range(1, 13):
+    gv = so.compute_gradients(((layer(x) - t) ** 2).mean())
+    so.apply_gradients(gv, gs)
+    if sched.is_update_iter(step):
+      m0, w0 = layer.mask.numpy().copy(), layer.weight.detach().cpu().numpy().copy()
+      g = layer.masked_weights.dense_grad.view(60, 50).cpu().numpy().copy()
+      mom0 = inner.state[layer.weight]['momentum_buffer'].cpu().numpy().copy()
+      sched.update(step)
+      frac = sched.get_drop_fraction(step)
+      assert sched.last_drop_fraction == frac and frac.dtype == np.float32
+      want_mask, want_w = orc.tf2_generic_mask_update(m0, w0, np.abs(m0 * w0), np.abs(g), frac)
+      assert np.array_equal(layer.mask.numpy(), want_mask)
+      assert layer.weight.detach().cpu().numpy().tobytes() == want_w.tobytes()
+      new = (want_mask == 1) & (m0 == 0)
+      mom1 = inner.state[layer.weight]['momentum_buffer'].cpu().numpy()
+      assert (mom1[new] == 0).all() and np.array_equal(mom1[~new], mom0[~new])       # reset_momentum (:156-162)
+      n_updates += 1
+  assert n_updates == 3 and gs.value == 12
+  # prune: score_grow = None -> the layer keeps its top n_ones - int(n_ones * f) by |mask * w|, nothing grows
+  m0, w0 = layer.mask.numpy().copy(), layer.weight.detach().cpu().numpy().copy()
+  sched.prune(0.25)
+  n_ones = int(m0.sum())
+  n_keep = n_ones - int(np.float32(n_ones) * np.float32(0.25))
+  order = np.argsort(-np.abs(m0 * w0).ravel(), kind='stable')
+  want = np.zeros(m0.size, np.float32)
+  want[order[:n_keep]] = 1
+  assert np.array_equal(layer.mask.numpy().ravel(), want)
+  assert layer.weight.detach().cpu().numpy().tobytes() == w0.tobytes()
