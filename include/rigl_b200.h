@@ -235,6 +235,10 @@ RIGL_API int rigl_bn_partial_rows(void);
 RIGL_API int rigl_masked_conv2d_fprop_bnstats(const rigl_conv_desc* d, const void* x, const void* packed,
                                               void* y_bf16, float* bn_partial, int* bn_rows_out, void* ws,
                                               size_t ws_bytes, void* stream);
+/* The statistics epilogue is used only where it is profitable (reduction length taps*cin >= 512, or >= 256 with
+ * <= 128 output channels; otherwise RIGL_ERR_UNSUPPORTED and the caller runs the plain call + a stats pass).
+ * on != 0: for every supported shape (tests; same as RIGL_BN_STATS_ALWAYS=1). */
+RIGL_API int rigl_set_bn_stats_always(int on);
 /* dx = conv^T(dy, mask*W). */
 RIGL_API int rigl_masked_conv2d_dgrad(const rigl_conv_desc* d, const void* dy, const void* packed,
                                       void* dx, void* ws, size_t ws_bytes, void* stream);

@@ -34,6 +34,32 @@ def max_pool_same(x, k=3, s=2):
   return F.max_pool2d(F.pad(x, (pw0, pw1, ph0, ph1), value=float('-inf')), k, s, 0)
 
 
+class _RoundBf16(torch.autograd.Function):
+  """x -> bf16(x) in the forward pass, g -> bf16(g) in the backward pass: the storage rounding of an activation
+  tensor (and of its gradient) on the bf16 training path of BASELINE C2-C5."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).float()
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).float()
+
+
+class _RoundGradBf16(torch.autograd.Function):
+  """identity forward, g -> bf16(g) backward (the fp32 logits: the device casts dL/dlogits to bf16 before the
+  classifier's dgrad / wgrad GEMMs)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.view_as(x)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).float()
+
+
 class _CpuNet(object):
   """Shared pieces: masked weights / masks / momentum slots by reference variable scope, batch-norm
   parameters in execution order (`self.bn_order`), dense (un-masked) parameters in `self.p`."""
@@ -48,8 +74,20 @@ class _CpuNet(object):
       self.mom[n] = torch.zeros(sh)
     self.bn, self.bn_order, self.p = {}, [], {}
     self.bn_init = None          # optional callable(key, channels) -> (gamma, beta) numpy
+    self.trace = None            # optional list: receives (key, BN output) in execution order (debugging)
+    # bf16_activations: every activation tensor the B200 path stores (conv outputs, BN / ReLU / residual outputs,
+    # pooled features) and its gradient are rounded to bf16 at the same points; arithmetic inside an op stays fp32.
+    # This is the bf16 configuration BASELINE.json names; False = the reference's fp32 CPU path (the timing port).
+    # A 50-layer batch-normalised network at initialisation amplifies ANY perturbation by ~1.2x per layer
+    # (profiles/r02_whole_step_noise_growth.md), so only an oracle that rounds where the device rounds can be
+    # compared layer by layer with it.
+    self.bf16_act = False
 
-  def _bn(self, x, key, relu=True, eps=1e-5):
+  def q(self, x):
+    return _RoundBf16.apply(x) if self.bf16_act else x
+
+  def _bn(self, x, key, relu=True, eps=1e-5, store=True):
+    """store=False: the BN output is not materialised on the device (it is consumed by a fused residual add)."""
     c = x.shape[1]
     if key not in self.bn:
       g, b = (np.ones(c, np.float32), np.zeros(c, np.float32)) if self.bn_init is None else self.bn_init(key, c)
@@ -57,12 +95,19 @@ class _CpuNet(object):
       self.bn_order.append(key)
     g, b = self.bn[key]
     x = F.batch_norm(x, None, None, g, b, training=True, momentum=0.1, eps=eps)
-    return F.relu(x) if relu else x
+    x = F.relu(x) if relu else x
+    if store:
+      x = self.q(x)
+    if self.trace is not None:
+      self.trace.append((key, x.detach()))
+    return x
 
   def _masked(self):
     return {n: (self.m[n] * self.w[n]).requires_grad_(True) for n in self.w}      # materialised every step
 
   def _finish(self, logits, labels, masked, label_smoothing):
+    if self.bf16_act:
+      logits = _RoundGradBf16.apply(logits)
     for t in list(self.p.values()) + [v for gb in self.bn.values() for v in gb]:
       t.grad = None
     loss = F.cross_entropy(logits, labels, label_smoothing=label_smoothing)
@@ -112,7 +157,7 @@ class CpuResNet50(_CpuNet):
     self.fc_bias = torch.zeros(num_classes)
 
   def _conv(self, x, name, masked, stride):
-    return _conv_tf(x, masked[name], stride, 'FIXED')
+    return self.q(_conv_tf(x, masked[name], stride, 'FIXED'))
 
   def forward_backward(self, images, labels):
     """Returns (loss, dense grads dict).  images [N,3,H,W] fp32."""
@@ -129,9 +174,9 @@ class CpuResNet50(_CpuNet):
           sc = self._bn(self._conv(x, p + 'bottleneck_projection_' + sfx, masked, s), sfx + 'p', relu=False)
         y = self._bn(self._conv(x, p + 'bottleneck_1_' + sfx, masked, 1), sfx + '1')
         y = self._bn(self._conv(y, p + 'bottleneck_2_' + sfx, masked, s), sfx + '2')
-        y = self._bn(self._conv(y, p + 'bottleneck_3_' + sfx, masked, 1), sfx + '3', relu=False)
-        x = F.relu(y + sc)
-    x = x.mean(dim=(2, 3))
+        y = self._bn(self._conv(y, p + 'bottleneck_3_' + sfx, masked, 1), sfx + '3', relu=False, store=False)
+        x = self.q(F.relu(y + sc))              # relu(BN(conv3) + shortcut): ONE fused kernel, one rounding
+    x = self.q(x.mean(dim=(2, 3)))
     logits = x @ masked[p + 'final_dense'] + self.fc_bias
     return self._finish(logits, labels, masked, 0.1)
 
@@ -168,17 +213,17 @@ class CpuWideResNet(_CpuNet):
 
   def forward_backward(self, images, labels, label_smoothing=0.0):
     masked = self._masked()
-    net = _conv_tf(images, self.p['conv_1'], 1, 'SAME')
+    net = self.q(_conv_tf(images, self.p['conv_1'], 1, 'SAME'))
     for i, (skip_name, a, b, stride) in enumerate(self.blocks):
       skip = net
       net = self._bn(net, 'b%d_a' % i)
       if skip_name is not None:
-        skip = _conv_tf(net, masked[skip_name], stride, 'VALID')
-      net = _conv_tf(net, masked[a], stride, 'SAME')
+        skip = self.q(_conv_tf(net, masked[skip_name], stride, 'VALID'))
+      net = self.q(_conv_tf(net, masked[a], stride, 'SAME'))
       net = self._bn(net, 'b%d_b' % i)
-      net = _conv_tf(net, masked[b], 1, 'SAME') + skip
+      net = self.q(self.q(_conv_tf(net, masked[b], 1, 'SAME')) + skip)
     net = self._bn(net, 'final')
-    logits = net.mean(dim=(2, 3)) @ masked['resnet_model/logits'] + self.p['logits_bias']
+    logits = self.q(net.mean(dim=(2, 3))) @ masked['resnet_model/logits'] + self.p['logits_bias']
     return self._finish(logits, labels, masked, label_smoothing)
 
 
@@ -210,12 +255,12 @@ class CpuMobileNetV1(_CpuNet):
 
   def forward_backward(self, images, labels, label_smoothing=0.1):
     masked = self._masked()
-    x = self._bn(_conv_tf(images, self.p['initial_conv'], 2, 'FIXED'), 'bn0')
+    x = self._bn(self.q(_conv_tf(images, self.p['initial_conv'], 2, 'FIXED')), 'bn0')
     for i, (f, stride) in enumerate(self.CFG):
-      x = F.conv2d(x, self.p['depthwise_%d' % i], stride=stride, padding=1, groups=x.shape[1])
+      x = self.q(F.conv2d(x, self.p['depthwise_%d' % i], stride=stride, padding=1, groups=x.shape[1]))
       x = self._bn(x, 'dw%d' % i)
-      x = self._bn(_conv_tf(x, masked['resnet_model/contraction_1x1_%d' % i], 1, 'FIXED'), 'pw%d' % i)
-    logits = x.mean(dim=(2, 3)) @ masked['resnet_model/final_dense'] + self.p['final_bias']
+      x = self._bn(self.q(_conv_tf(x, masked['resnet_model/contraction_1x1_%d' % i], 1, 'FIXED')), 'pw%d' % i)
+    logits = self.q(x.mean(dim=(2, 3))) @ masked['resnet_model/final_dense'] + self.p['final_bias']
     return self._finish(logits, labels, masked, label_smoothing)
 
 

@@ -179,6 +179,12 @@ extern "C" int rigl_masked_conv2d_fprop(const rigl_conv_desc* d, const void* x, 
 
 extern "C" int rigl_bn_partial_rows(void) { return tc_max_ctas(); }
 
+extern "C" int rigl_set_bn_stats_always(int on) {
+  tc_set_bn_stats_always(on != 0);
+  tc_set_bn_stats_debug(on >> 4);       // (development: bits 4.. select partial variants of the statistics code)
+  return RIGL_OK;
+}
+
 extern "C" int rigl_masked_conv2d_fprop_bnstats(const rigl_conv_desc* d, const void* x, const void* packed,
                                                 void* y_bf16, float* bn_partial, int* bn_rows_out, void* ws,
                                                 size_t ws_bytes, void* stream) {

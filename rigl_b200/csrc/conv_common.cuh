@@ -58,6 +58,8 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
              const float* bias, void* ws, size_t ws_bytes, cudaStream_t s, float* bn_partial = nullptr,
              int* bn_rows = nullptr);
 int tc_max_ctas();
+void tc_set_bn_stats_always(bool on);
+void tc_set_bn_stats_debug(int v);
 int tc_dgrad(const ConvGeom& g, const void* dy, const void* packed, void* dx, void* ws,
              size_t ws_bytes, cudaStream_t s);
 int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float beta, void* ws,

@@ -72,6 +72,7 @@ struct IgemmParams {
   int tma_store;                    // 1: epilogue stages bf16 tiles in smem and TMA-stores them
   float* bn_partial;                // optional [gridDim.x][2][N]: per-CTA column sums / sums of squares of D
   int pair_local;                   // CTA-pair kernel: each CTA's TMA completes on its OWN barrier (see k_igemm_kmajor2)
+  int stats_dbg;                    // development: 1 = statistics without the global REDs, 2 = without the smem pass
 };
 
 struct TMaps4 {
@@ -124,13 +125,14 @@ __device__ __forceinline__ bool build_live_mask(const IgemmParams& p, int n_tile
 // each table entry is only ever touched by one lane of one warp, in tile order, so the fp32 sums are deterministic.
 // Rows outside the pixel grid are written as zeros by their owner (see the staging loops), so they do not count.
 __device__ __forceinline__ void slab_bn_stats(uint32_t slab, int quad, int lane, float* __restrict__ bn_row, int co0,
-                                              int n) {
+                                              int n, int dbg) {
   const int cp = lane & 7, g = lane >> 3;
   const uint32_t chunk = (uint32_t)(2 * quad + (cp >> 2));
   const uint32_t word = (uint32_t)(cp & 3) * 4u;
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int n_it = (dbg & 2) ? 0 : 32;
 #pragma unroll 8
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < n_it; ++i) {
     const uint32_t row = (uint32_t)(32 * g + ((i + 2 * g) & 31));
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slab + row * 128u + (((chunk ^ (row & 7u)) << 4) | word)));
@@ -144,7 +146,7 @@ __device__ __forceinline__ void slab_bn_stats(uint32_t slab, int quad, int lane,
     q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
   }
   const int co = co0 + 16 * quad + 2 * cp;
-  if (g == 0 && co < n) {          // (n is a multiple of 8 on this path, so co + 1 < n as well)
+  if (g == 0 && co < n && !(dbg & 1)) {          // (n is a multiple of 8 on this path, so co + 1 < n as well)
     atomicAdd(bn_row + co, s0); atomicAdd(bn_row + co + 1, s1);
     atomicAdd(bn_row + n + co, q0); atomicAdd(bn_row + n + co + 1, q1);
   }
@@ -340,7 +342,7 @@ k_igemm_kmajor(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CUt
             tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
-          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N);   // next to the bulk store's own read
+          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N, p.stats_dbg);   // next to the bulk store's own read
           ++slab_ctr;
         }
       } else {
@@ -649,7 +651,7 @@ k_igemm_kmajor2(const __grid_constant__ TMaps4 amaps, const __grid_constant__ CU
             tma_store_4d(&omap, slab, co0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
-          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N);   // next to the bulk store's own read
+          if (bn_row) slab_bn_stats(slab, quad, lane, bn_row, co0, p.N, p.stats_dbg);   // next to the bulk store's own read
           ++slab_ctr;
         }
       } else {
@@ -899,6 +901,7 @@ static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
 static bool g_pair_local = false;   // RIGL_PAIR_LOCALBAR=1: per-CTA full barriers + a forwarded arrive (measured 2.5x SLOWER than signalling the leader directly; kept as a documented negative result)
+static bool g_bn_stats_always = false;   // RIGL_BN_STATS_ALWAYS=1: epilogue statistics for every supported shape (tests)
 static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
 static int g_halo_t = 0, g_halo_nbuf = 0;   // RIGL_HALO_CFG=T,NBUF: tuning override for the halo kernels
 static bool g_cluster_mc = false;   // RIGL_CLUSTER_MC=1 enables the 2-CTA multicast clusters (measured neutral
@@ -921,6 +924,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_CLUSTER_MC")) g_cluster_mc = (e[0] == '1');
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_BN_STATS_ALWAYS")) g_bn_stats_always = (e[0] == '1');
   if (const char* e = getenv("RIGL_PAIR_LOCALBAR")) g_pair_local = (e[0] == '1');
   if (const char* e = getenv("RIGL_HALO_CFG")) sscanf(e, "%d,%d", &g_halo_t, &g_halo_nbuf);
   int dev = 0;
@@ -1143,6 +1147,10 @@ static int pick_bn(int n_out, long long m_tiles) {
   return 64;
 }
 
+void tc_set_bn_stats_always(bool on) { g_bn_stats_always = on; }
+static int g_stats_dbg = 0;
+void tc_set_bn_stats_debug(int v) { g_stats_dbg = v; }
+
 int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, float* y_f32, const float* bias,
              void* ws, size_t ws_bytes, cudaStream_t s, float* bn_partial, int* bn_rows) {
   (void)ws; (void)ws_bytes;
@@ -1160,6 +1168,17 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
       return halo_launch_kmajor(hp, x, g.cin, g.x_pitch, pk + L.off_fprop, L.cin_pad, g.cout, y, g.cout, false, s);
     }
   }
+  if (bn_partial != nullptr && !g_bn_stats_always) {
+    // Measured on B200 (ResNet-50 b256, profiles/r02_bn_stats_epilogue.md): the statistics are free when the tile's
+    // main loop is long enough to hide them (reduction length K = taps * cin >= 512), and cost about what the
+    // separate stats pass costs -- or more -- for the short-K / wide-output layers whose epilogue is the
+    // bottleneck (1x1 convs with K <= 128; K = 256 with more than 128 output channels).
+    const int K = g.taps() * g.cin;
+    if (!(K >= 512 || (K >= 256 && g.cout <= 128))) {
+      set_error("fused BN statistics: not profitable for this shape (K = %d, cout = %d)", K, g.cout);
+      return RIGL_ERR_UNSUPPORTED;
+    }
+  }
   IgemmParams p = {};
   choose_box(g.out_w, g.out_h, g.batch, 128, &p.bw, &p.bh, &p.bn);
   p.GW = g.out_w; p.GH = g.out_h; p.NB = g.batch;
@@ -1171,6 +1190,7 @@ int tc_fprop(const ConvGeom& g, const void* x, const void* packed, void* y, floa
   p.nnz = reinterpret_cast<const uint32_t*>(pk + L.off_nnz);
   p.nnz_tap_stride = L.n_tiles * L.k_tiles; p.nnz_n_stride = L.k_tiles; p.nnz_k_stride = 1;
   p.bn_partial = bn_partial;            // (decides the kernel variant, hence the B box: set before the maps)
+  p.stats_dbg = g_stats_dbg;
   TMaps4 amaps;
   const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
   bool made[4] = {false, false, false, false};

@@ -172,7 +172,7 @@ def test_maxpool_same_forward_backward(shape):
 # space-to-depth stem have no statistics epilogue and fall back to the stats pass; the rest covers the CTA-pair and
 # single-CTA kernels, several N tiles (cout 512 / 1024), pixel grids that do not fill their boxes (7x7, 13x9) and
 # problems with many tiles per CTA.
-@pytest.mark.parametrize('case', [(4, 16, 16, 64, 128, 3, 1, False), (2, 28, 28, 128, 256, 1, 1, True),
+@pytest.mark.parametrize('case', [(4, 56, 56, 64, 64, 3, 1, None), (4, 16, 16, 64, 128, 3, 1, True), (2, 28, 28, 128, 256, 1, 1, True),
                                   (8, 14, 14, 64, 64, 3, 2, True), (3, 32, 32, 3, 64, 7, 2, False),
                                   (1, 8, 8, 64, 64, 1, 1, True), (16, 7, 7, 256, 1024, 1, 1, True),
                                   (5, 13, 9, 128, 512, 1, 1, True), (64, 56, 56, 64, 256, 1, 1, True),
@@ -190,17 +190,39 @@ def test_conv_epilogue_bn_stats_match_stats_pass(case):
   x = torch.randn(n, cin, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   outs = []
   old = layers.FUSE_BN_STATS
+  from rigl_b200 import _cabi
+  _cabi.lib().rigl_set_bn_stats_always(1)        # every supported shape, not only the profitable ones
   for fused in (True, False):
     layers.FUSE_BN_STATS = fused
     try:
       bn = FusedBatchNormReLU(cout, relu=True, device=DEV)
       y = conv(x)
-      assert (conv.bn_partial is not None) == (fused and expect_epilogue)
+      if expect_epilogue is not None:       # (None: halo-kernel eligibility decides; either way the results must agree)
+        assert (conv.bn_partial is not None) == (fused and expect_epilogue)
       outs.append((bn(y, producer=conv).float(), bn.running_mean.clone(), bn.running_var.clone()))
     finally:
       layers.FUSE_BN_STATS = old
+      if not fused:
+        _cabi.lib().rigl_set_bn_stats_always(0)
   (a, ma, va), (b, mb, vb) = outs
   # same bf16 values summed in a different order: the statistics agree to fp32 summation noise
   assert float((ma - mb).abs().max()) <= 1e-5 * float(vb.sqrt().max()) * 10 + 1e-6
   assert torch.allclose(va, vb, rtol=1e-4, atol=1e-6)
   assert float((a - b).abs().max()) <= 2 ** -7 * float(b.abs().max()) + 1e-3
+
+
+def test_conv_epilogue_bn_stats_only_where_profitable():
+  """Default policy: short reductions with wide outputs (epilogue-bound layers) keep the separate stats pass."""
+  from rigl_b200 import layers, pruning
+  pruning.reset_default_registry()
+  old, layers.FUSE_BN_STATS = layers.FUSE_BN_STATS, True
+  try:
+    for cin, cout, k, expect in ((64, 256, 1, False), (128, 512, 1, False), (256, 512, 1, False), (256, 64, 1, True),
+                                (512, 128, 1, True), (128, 128, 3, True)):
+      conv = layers.SparseConv2d(cin, cout, k, padding='FIXED', name='c%d_%d' % (cin, cout), device=DEV)
+      conv.collect_bn_stats = True
+      x = torch.randn(4, cin, 14, 14, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+      conv(x)
+      assert (conv.bn_partial is not None) == expect, (cin, cout, k)
+  finally:
+    layers.FUSE_BN_STATS = old

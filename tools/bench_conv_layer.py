@@ -26,6 +26,8 @@ SHAPES = {
     'r50_33c3': [(256, 14, 14, 256, 256, 3, 1)],
     'r50_3x3': [(256, 56, 56, 64, 64, 3, 1), (256, 28, 28, 128, 128, 3, 1), (256, 14, 14, 256, 256, 3, 1),
                 (256, 7, 7, 512, 512, 3, 1)],
+    'stats': [(256, 56, 56, 64, 256, 1, 1), (256, 28, 28, 128, 512, 1, 1), (256, 56, 56, 256, 64, 1, 1),
+              (256, 28, 28, 512, 128, 1, 1)],
     'r50_1x1': [(256, 56, 56, 64, 256, 1, 1), (256, 56, 56, 256, 64, 1, 1), (256, 28, 28, 512, 128, 1, 1),
                 (256, 14, 14, 1024, 256, 1, 1), (256, 7, 7, 2048, 512, 1, 1)],
 }
@@ -72,7 +74,17 @@ def main():
            for _ in range(copies)]
     dw = torch.empty(k * k * cin * cout, dtype=torch.float32, device=DEV)
     flops = 2.0 * n * ho * wo * k * k * cin * cout
-    ops = (('fprop', lambda i: layer._fprop(xs[i % copies], None, False)),
+    from rigl_b200 import layers as L, _cabi
+    def fprop_stats(i):
+      L.FUSE_BN_STATS, layer.collect_bn_stats = True, True
+      layer.train()
+      try:
+        return layer._fprop(xs[i % copies], None, False)
+      finally:
+        L.FUSE_BN_STATS, layer.collect_bn_stats = False, False
+    _cabi.lib().rigl_set_bn_stats_always(1 | (int(os.environ.get('STATS_DBG', '0')) << 4))
+    L.FUSE_BN_STATS = False
+    ops = (('fprop', lambda i: layer._fprop(xs[i % copies], None, False)), ('fprop_stats', fprop_stats),
            ('dgrad', lambda i: layer._dgrad(dys[i % copies], xs[i % copies])),
            ('wgrad', lambda i: layer._wgrad(xs[i % copies], dys[i % copies], dw, False)))
     for name, fn in ops:
