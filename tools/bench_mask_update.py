@@ -41,7 +41,8 @@ def main():
   ap.add_argument('--tag', default='r50_erk80')
   ap.add_argument('--iters', type=int, default=20)
   ap.add_argument('--warmup', type=int, default=3)
-  ap.add_argument('--noise', action='store_true')
+  ap.add_argument('--noise', action='store_true', help='drop-score noise read from a tensor')
+  ap.add_argument('--inkernel-noise', action='store_true', help='drop-score noise drawn inside the kernels')
   args = ap.parse_args()
   specs = build_layers(args.tag, args.noise)
   total_n = sum(s['mask'].size for s in specs)
@@ -52,7 +53,10 @@ def main():
     flush.zero_()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    eng.run(specs, np.float32(0.3))
+    if args.inkernel_noise:
+      eng.run(specs, np.float32(0.3), noise_std=1e-5, noise_seed=(77 << 32) | it)
+    else:
+      eng.run(specs, np.float32(0.3))
     stop.record()
     torch.cuda.synchronize()
     if it >= args.warmup:
@@ -61,7 +65,7 @@ def main():
   ms = float(np.median(times))
   alg_bytes = (8.25 + (4 if args.noise else 0)) * total_n
   print(json.dumps({'bench': 'mask_update', 'tag': args.tag, 'layers': len(specs), 'weights': total_n,
-                    'noise': args.noise, 'ms_median': ms, 'ms_min': float(min(times)),
+                    'noise': args.noise, 'inkernel_noise': args.inkernel_noise, 'ms_median': ms, 'ms_min': float(min(times)),
                     'algorithmic_GBps': alg_bytes / ms / 1e6, 'workspace_MB': eng.workspace_bytes / 2 ** 20,
                     'max_drop_candidates': max(s[3] for s in stats),
                     'max_grow_candidates': max(s[4] for s in stats),
