@@ -22,7 +22,8 @@
 //                      grow histogram; picks the grow threshold bin
 //   E  k_scan_grow   : definite grows -> mask2 bit, weight/slot re-init at new
 //                      connections; threshold bin -> candidates
-//   F  k_resolve<1>  : exact grow cut; writes mask = mask1 | mask2
+//   F  k_resolve<1>  : exact grow cut (ORs the selected candidates into mask1)
+//   G  k_publish_mask: mask = mask1 | mask2, whole grid
 // Selection is by exact integer comparison of (key, index) composites, hence
 // deterministic and independent of atomic ordering.
 //
@@ -178,6 +179,7 @@ __device__ __forceinline__ void flush_hist(const uint32_t* sh, uint32_t* gh) {
 // ----------------------------------------------------------------------------
 // A: histogram of drop keys
 // ----------------------------------------------------------------------------
+template <bool kGenNoise>       // in-kernel noise is a separate instantiation: the plain path keeps its schedule
 __global__ void __launch_bounds__(kScanThreads, 4)
 k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
@@ -188,7 +190,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool explicit_score = L.sdrop != nullptr;
-  const bool gen_noise = L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
+  const bool gen_noise = kGenNoise && L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
   const bool has_noise = (L.noise != nullptr && !explicit_score) || gen_noise;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
@@ -346,6 +348,7 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
 // ----------------------------------------------------------------------------
 // C: classify against the drop threshold bin, build mask1, grow histogram
 // ----------------------------------------------------------------------------
+template <bool kGenNoise>
 __global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
@@ -360,7 +363,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const uint32_t bucket = (uint32_t)st->drop_bucket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool explicit_score = L.sdrop != nullptr;
-  const bool gen_noise = L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
+  const bool gen_noise = kGenNoise && L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
   const bool has_noise = (L.noise != nullptr && !explicit_score) || gen_noise;
   const float* __restrict__ wsrc = explicit_score ? L.sdrop : L.w;
   const uint32_t n = L.n;
@@ -583,13 +586,21 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
       st->grow_need = out[1];
       st->n_cand_grow = (int32_t)out[2];
     }
-  } else {
-    // publish: mask <- mask1 | mask2 (atomicOr results live in L2)
-    __threadfence();
-    __syncthreads();
-    const uint32_t words = (L.n + 31) >> 5;
-    for (uint32_t i = tid; i < words; i += kResolveThreads) L.mask[i] = __ldcg(mask1 + i);
   }
+  // (grow: the final bitmap mask1 | mask2 is published by k_publish_mask over the whole grid -- one block per layer
+  //  copying a 2.4 M-bit bitmap was a third of this kernel's time)
+}
+
+// G: mask <- mask1 (| mask2, already OR-ed in by k_scan_grow / k_resolve<grow>), all layers, full grid
+__global__ void __launch_bounds__(kScanThreads)
+k_publish_mask(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws) {
+  const BlockTask task = tasks[blockIdx.x];
+  const LayerDev L = layers[task.layer];
+  const uint32_t* mask1 = reinterpret_cast<const uint32_t*>(ws + L.off_mask1);
+  const uint32_t words = (L.n + 31) >> 5;
+  const uint32_t w0 = task.start >> 5;
+  for (uint32_t i = w0 + threadIdx.x; i < min(words, w0 + (uint32_t)(kChunk >> 5)); i += kScanThreads)
+    L.mask[i] = __ldcg(mask1 + i);
 }
 
 // ----------------------------------------------------------------------------
@@ -774,11 +785,14 @@ static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm, void* 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   RIGL_CUDA(cudaMemsetAsync(ws, 0, plan->zero_bytes, stream));
-  k_hist_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  const bool gen = prm.noise_std > 0.f;
+  if (gen) k_hist_drop<true><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  else k_hist_drop<false><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
   RIGL_LAUNCH_CHECK("k_hist_drop");
   k_pick_drop<<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_pick_drop");
-  k_scan_drop<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  if (gen) k_scan_drop<true><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  else k_scan_drop<false><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
   RIGL_LAUNCH_CHECK("k_scan_drop");
   k_resolve<false><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_resolve<drop>");
@@ -786,6 +800,8 @@ static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm, void* 
   RIGL_LAUNCH_CHECK("k_scan_grow");
   k_resolve<true><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
   RIGL_LAUNCH_CHECK("k_resolve<grow>");
+  k_publish_mask<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws);
+  RIGL_LAUNCH_CHECK("k_publish_mask");
   return RIGL_OK;
 }
 

@@ -133,6 +133,8 @@ def _compare_step(tag, model, net, images, labels, harness, loss_tol, grad_tol, 
   _load(model, net)
   # (1) every masked layer alone, on the tensors of this step: tight bounds
   forced = _teacher_forced_layers(model, net)
+  for l in model.registry.layers():
+    l.weight.grad = None                  # (the replay left masked gradients behind; the step below owns them)
   # (2) the free-running step: bounded by how the network amplifies rounding flips (see the module docstring)
   xd = images.to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
   yd = labels.to(DEV)
