@@ -12,10 +12,15 @@ What is compared and how tight it can be ("whole-step bound"):
     of ~1.3 -- measured on the CPU with no kernel involved (tools/noise_growth.py ->
     profiles/r02_whole_step_noise_growth.md), and the CUDA step shows the same figures.
   * With matching rounding points what remains is fp32 summation order plus the rare bf16 rounding flips it
-    causes, amplified the same way: per-layer relative L2 of the dense gradients of order 1e-2.  The bounds below
-    are ~3x what was MEASURED on a B200 (recorded by this test into gpurun_out/whole_step_parity_<model>.json
-    when that directory exists); a wrong tap, stride, padding, transposed operand, BN statistic or residual
-    wiring gives errors of order 1 in every layer downstream of it.
+    causes (~1e-4 of a tensor per rounding point), amplified the same way.  Two checks follow from that:
+    (1) TEACHER-FORCED: every masked layer replayed alone on the oracle's tensors of this very step -- no
+        amplification, tight bounds (dense wgrad <= 2e-5, fprop / dgrad <= 1e-3 relative L2);
+    (2) FREE-RUNNING: the whole CUDA step against the oracle's, bounded by ~3x the MEASURED figures (ResNet-50
+        with the last BN of each block near the reference's zero init: median 0.15 / max 0.18; WRN-22-2: 0.08 /
+        0.09; MobileNet-v1, a plain 27-BN stack with nothing to damp the growth: 0.09 at the classifier rising to
+        0.7 at the first layer -- only its last two layers are bounded).  A wrong tap, stride, padding, transposed
+        operand, BN statistic or residual wiring gives errors of order 1 in every layer downstream of it and
+        fails (1) outright.  Measurements are recorded into gpurun_out/whole_step_parity_<model>.json.
   * Mask updates are integer work: given the dense gradients the CUDA step produced, the oracle's drop/grow
     (base.py:276-343 restated) must give BIT-IDENTICAL masks, weights and momentum slots; the optimizer step is
     checked against the oracle's Nesterov-momentum arithmetic on the same gradients.
@@ -80,13 +85,15 @@ def _nhwc_dev(t):
   return t.detach().to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 
 
-def _teacher_forced_layers(model, net, tol_act=2e-3, tol_dense=2e-4):
+def _teacher_forced_layers(model, net, tol_act=1e-3, tol_dense=2e-5):
   """Every masked layer of the model, replayed ALONE through the CUDA kernels on the tensors of the oracle's real
   train step: its stored (bf16) input activation x and the stored (bf16) gradient dy of its output.  Independent
   of how the network amplifies perturbations, so the bounds are tight:
-    fprop / dgrad (bf16 outputs): relative L2 <= 2e-3 -- the two sides round fp32 accumulators that differ in
-      summation order, so a small fraction of elements lands on the neighbouring bf16 value;
-    DENSE wgrad (fp32 accumulators, identical bf16 operands): relative L2 <= 2e-4 (measured ~1e-6..1e-5)."""
+    fprop / dgrad (bf16 outputs): relative L2 <= 1e-3 -- the two sides round fp32 accumulators that differ in
+      summation order, so a small fraction of elements lands on the neighbouring bf16 value
+      (measured on B200: <= 6.4e-5 fprop, <= 1.7e-4 dgrad over all layers of the three models);
+    DENSE wgrad (fp32 accumulators, identical bf16 operands): relative L2 <= 2e-5, the north-star's 1e-5-class
+      bound (measured: <= 7.8e-7 ResNet-50, 2.6e-6 WRN-22-2, 6.4e-7 MobileNet-v1)."""
   out = {}
   for l in model.registry.layers():
     x, y, stride, padding = net.record[l.scope]
@@ -214,7 +221,7 @@ def test_resnet50_step_vs_cpu_oracle():
   images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
   labels = torch.randint(0, 1000, (8,))
   h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
-  _compare_step('resnet50', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.12, label_smoothing=None)
+  _compare_step('resnet50', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.5, label_smoothing=None)
   _check_update_steps(model, h, images, labels, 4, [0, 2])
 
 
@@ -244,6 +251,6 @@ def test_mobilenet_v1_step_vs_cpu_oracle():
   images = torch.randn(8, 3, 64, 64).to(torch.bfloat16)
   labels = torch.randint(0, 1000, (8,))
   h = workloads.TrainHarness(model, lr=0.05, frequency=2, end_step=100)
-  _compare_step('mobilenet_v1', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.35, label_smoothing=0.1,
-                last_layers=3)
+  _compare_step('mobilenet_v1', model, net, images, labels, h, loss_tol=2e-2, grad_tol=0.6, label_smoothing=0.1,
+                last_layers=2)
   _check_update_steps(model, h, images, labels, 4, [0, 2])
