@@ -429,6 +429,9 @@ struct WgradParams {
   int m_tiles, n_tiles;
   float* out;                       // [splits][taps][ci][co] partials (or dw itself when splits == 1)
   long long split_stride;           // elements between split slices
+  int* counters;                    // split-K fix-up: arrivals per output tile (zeroed by the launcher), or null
+  float* dw;                        // fix-up target [taps][ci][co]
+  float beta;                       // dw <- beta * dw + sum of the partials
 };
 
 // ----------------------------------------------------------------------------
@@ -721,6 +724,7 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tmap(&xmaps.a[i]);
@@ -859,6 +863,42 @@ k_igemm_wgrad(const __grid_constant__ TMaps4 xmaps, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (p.counters != nullptr) {
+        // ---- split-K fix-up inside the kernel: the unit that arrives LAST at an output tile sums the partial
+        // tiles of all splits in split order (deterministic) while they are still in L2, and writes dw.  Replaces
+        // one k_splitk_reduce launch per layer.
+        __threadfence();                                   // my part of this unit's partial tile is visible
+        named_bar_sync(2, 128);
+        if (warp == 2 && lane == 0) {
+          int last = 0;
+          if (live) {
+            int* ctr = p.counters + (mi * p.n_tiles + n_tile);
+            last = (atomicAdd(ctr, 1) == p.splits - 1) ? 1 : 0;
+            if (last) *ctr = 0;                            // every split has arrived: re-arm for the next launch
+          }
+          s_last = last;
+        }
+        named_bar_sync(2, 128);
+        if (s_last) {
+          __threadfence();
+          const int m0 = (mi % p.m_tiles) * kBM;
+          const long long tap_off = (long long)p.taps[tap_idx].b_tap * p.ci;
+          for (int rr = warp - 2; rr < kBM && m0 + rr < p.ci; rr += 4) {       // warp per row, lanes over columns
+            const long long row_off = (tap_off + m0 + rr) * p.co;
+            for (int c = 4 * lane; c < BN; c += 128) {
+              const int co = n_tile * BN + c;
+              if (co >= p.co) break;
+              float4 a = p.beta != 0.f ? *reinterpret_cast<const float4*>(p.dw + row_off + co)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.out + (long long)sp * p.split_stride + row_off + co));
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+              }
+              *reinterpret_cast<float4*>(p.dw + row_off + co) = a;
+            }
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -901,6 +941,7 @@ static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
 static bool g_pair_local = false;   // RIGL_PAIR_LOCALBAR=1: per-CTA full barriers + a forwarded arrive (measured 2.5x SLOWER than signalling the leader directly; kept as a documented negative result)
+static bool g_wgrad_fixup = true;        // RIGL_WGRAD_FIXUP=0: separate k_splitk_reduce launch per layer
 static bool g_bn_stats_always = false;   // RIGL_BN_STATS_ALWAYS=1: epilogue statistics for every supported shape (tests)
 static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
 static int g_halo_t = 0, g_halo_nbuf = 0;   // RIGL_HALO_CFG=T,NBUF: tuning override for the halo kernels
@@ -925,6 +966,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
   if (const char* e = getenv("RIGL_BN_STATS_ALWAYS")) g_bn_stats_always = (e[0] == '1');
+  if (const char* e = getenv("RIGL_WGRAD_FIXUP")) g_wgrad_fixup = !(e[0] == '0');
   if (const char* e = getenv("RIGL_PAIR_LOCALBAR")) g_pair_local = (e[0] == '1');
   if (const char* e = getenv("RIGL_HALO_CFG")) sscanf(e, "%d,%d", &g_halo_t, &g_halo_nbuf);
   int dev = 0;
@@ -1025,6 +1067,11 @@ static size_t wgrad_ws_elems(const ConvGeom& g, int* splits_out, int* bps_out, i
   return (size_t)splits * g.taps() * g.cin * g.cout;
 }
 
+static size_t wgrad_counter_bytes(const ConvGeom& g, int bn_tile) {
+  const size_t tiles = (size_t)g.taps() * ((g.cin + kBM - 1) / kBM + 1) * ((g.cout + bn_tile - 1) / bn_tile);
+  return (tiles * sizeof(int) + 255) / 256 * 256;
+}
+
 // Wider N tiles halve the L2->smem bytes per FLOP (the wgrad main loop is L2-bandwidth bound:
 // K blocks are only 64 pixels deep).
 static int wgrad_bn_tile(const ConvGeom& g) {
@@ -1042,7 +1089,7 @@ size_t tc_workspace_bytes(const ConvGeom& g) {
   size_t elems = wgrad_ws_elems(g, nullptr, nullptr, bw, bh, bn, wgrad_bn_tile(g));
   HaloParams hp;
   if (halo_wgrad_ok(g, &hp)) { const size_t e = halo_wgrad_ws_elems(g, hp); if (e > elems) elems = e; }
-  return elems * sizeof(float) + 256;
+  return elems * sizeof(float) + wgrad_counter_bytes(g, wgrad_bn_tile(g)) + 256;
 }
 
 // With the 2-CTA multicast each CTA fetches half of the weight tile (B box = bn_tile/2 rows).
@@ -1381,12 +1428,17 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
   const bool direct = (p.splits == 1 && beta == 0.f);
   if (!direct) {
     const size_t need = elems * sizeof(float);
-    float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    if (ws == nullptr || ws_bytes < need + 256) {
-      set_error("rigl_conv2d_wgrad_dense: workspace %zu < required %zu", ws_bytes, need + 256);
+    const size_t ctr_bytes = wgrad_counter_bytes(g, bn_tile);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    if (ws == nullptr || ws_bytes < need + ctr_bytes + 256) {
+      set_error("rigl_conv2d_wgrad_dense: workspace %zu < required %zu", ws_bytes, need + ctr_bytes + 256);
       return RIGL_ERR_WORKSPACE;
     }
-    p.out = wsf; p.split_stride = n_w;
+    p.out = reinterpret_cast<float*>(base + ctr_bytes); p.split_stride = n_w;
+    if (g_wgrad_fixup) {
+      p.counters = reinterpret_cast<int*>(base); p.dw = dw; p.beta = beta;
+      RIGL_CUDA(cudaMemsetAsync(p.counters, 0, ctr_bytes, s));     // (the kernel re-arms them, but the scratch is the caller's)
+    }
   } else {
     p.out = dw; p.split_stride = 0;
   }
@@ -1415,7 +1467,7 @@ int tc_wgrad(const ConvGeom& g, const void* x, const void* dy, float* dw, float 
        : (bn_tile == 128) ? launch_wgrad<128, 6>(xmaps, dymap, p, s)
                           : launch_wgrad<64, 8>(xmaps, dymap, p, s);
   if (rc != RIGL_OK) return rc;
-  if (!direct) {
+  if (!direct && p.counters == nullptr) {
     const long long threads = (n_w + 3) / 4;
     k_splitk_reduce<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p.out, p.split_stride, p.splits, dw, n_w, beta);
     RIGL_LAUNCH_CHECK("k_splitk_reduce");

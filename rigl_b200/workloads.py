@@ -307,6 +307,15 @@ class TrainHarness(object):
       overlap_wgrad = os.environ.get('RIGL_WGRAD_OVERLAP', '1') != '0' 
     self._overlap = bool(overlap_wgrad)
     self._sx, self._sy = images.clone(), labels.clone()
+    ok = self._capture(warmup)
+    if not ok and self.dp is not None and self._dp_overlap:
+      # the collectives could not be captured on this stack: capture the step without them and all-reduce
+      # (blocking, one call) between the two replays instead of falling back to the eager step
+      self._dp_overlap = False
+      ok = self._capture(warmup)
+    return ok
+
+  def _capture(self, warmup):
     try:
       side = torch.cuda.Stream()
       side.wait_stream(torch.cuda.current_stream())

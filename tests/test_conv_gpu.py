@@ -354,3 +354,31 @@ def test_batched_pack_equals_per_layer_pack():
     for g, w in zip(got, ws):
       assert torch.equal(g, w), l.scope
   layers._PACKED_AHEAD.clear()
+
+
+@pytest.mark.parametrize('case', [CONV_CASES[8], CONV_CASES[9], CONV_CASES[11]])
+def test_conv_wgrad_separate_splitk_reduce_path(case):
+  """RIGL_WGRAD_FIXUP=0: the dense wgrad's split-K partials are summed by a separate k_splitk_reduce launch instead
+  of by the last-arriving CTA inside the wgrad kernel (the default).  Same oracle, same tolerance."""
+  import os, subprocess, sys
+  code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_conv_gpu as t; '
+          't._conv_case(%r, False); print("RED_OK")' % (os.path.dirname(os.path.dirname(__file__)),
+                                                        os.path.dirname(__file__), case))
+  env = dict(os.environ, RIGL_WGRAD_FIXUP='0')
+  out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert 'RED_OK' in out.stdout, out.stdout[-1500:]
+
+
+def test_conv_wgrad_accumulates_over_backward_passes():
+  """beta = 1: a second backward before the gradients are consumed ADDS to the dense gradient (the in-kernel
+  split-K fix-up reads dw back), bit-identically to doing it twice on the host."""
+  pruning.reset_default_registry()
+  torch.manual_seed(3)
+  layer = SparseConv2d(128, 256, 3, padding='FIXED', name='acc', device=DEV)
+  x = torch.randn(8, 128, 14, 14, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  dy = torch.randn(8, 256, 14, 14, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+  layer.masked_weights.fresh = False
+  layer(x).backward(dy)
+  once = layer.masked_weights.dense_grad.clone()
+  layer(x).backward(dy)                       # fresh is still True: accumulates
+  assert torch.equal(layer.masked_weights.dense_grad, once + once)
