@@ -371,7 +371,7 @@ def test_conv_wgrad_separate_splitk_reduce_path(case):
 
 def test_conv_wgrad_accumulates_over_backward_passes():
   """beta = 1: a second backward before the gradients are consumed ADDS to the dense gradient (the in-kernel
-  split-K fix-up reads dw back), bit-identically to doing it twice on the host."""
+  split-K fix-up reads dw back and adds the partials to it in split order)."""
   pruning.reset_default_registry()
   torch.manual_seed(3)
   layer = SparseConv2d(128, 256, 3, padding='FIXED', name='acc', device=DEV)
@@ -381,4 +381,4 @@ def test_conv_wgrad_accumulates_over_backward_passes():
   layer(x).backward(dy)
   once = layer.masked_weights.dense_grad.clone()
   layer(x).backward(dy)                       # fresh is still True: accumulates
-  assert torch.equal(layer.masked_weights.dense_grad, once + once)
+  assert torch.allclose(layer.masked_weights.dense_grad, once + once, rtol=1e-5, atol=1e-5 * float(once.abs().max()))
