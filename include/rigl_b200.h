@@ -303,14 +303,17 @@ RIGL_API int rigl_bn_forward_train(const void* y, const void* residual, const fl
                                    const float* beta, int64_t rows, int channels, float eps,
                                    float momentum, int relu, float* running_mean, float* running_var,
                                    float* save_mean, float* save_rstd, float* save_scale,
-                                   float* save_shift, void* out, void* ws, size_t ws_bytes, void* stream);
+                                   float* save_shift, void* out, void* ws, size_t ws_bytes, void* relu_bits,
+                                   void* stream);
+/* relu_bits (optional, uint8 [rows*channels/8]): bit k of byte i <- out[8i+k] > 0.  The residual-form backward
+ * needs nothing else of the block output, so it reads this bitmap (1/16 of the bytes) instead of re-reading it. */
 /* Training forward from conv-epilogue partial sums (rigl_masked_conv2d_fprop_bnstats). */
 RIGL_API int rigl_bn_forward_train_partials(const void* y, const void* residual, const float* gamma,
                                             const float* beta, const float* partial, int partial_rows,
                                             int64_t rows, int channels, float eps, float momentum, int relu,
                                             float* running_mean, float* running_var, float* save_mean,
                                             float* save_rstd, float* save_scale, float* save_shift, void* out,
-                                            void* stream);
+                                            void* relu_bits, void* stream);
 /* Inference / given statistics: out = [relu](y*scale + shift (+ residual)). */
 RIGL_API int rigl_bn_apply(const void* y, const void* residual, const float* scale, const float* shift,
                            int64_t rows, int channels, int relu, void* out, void* stream);
@@ -329,7 +332,8 @@ RIGL_API int rigl_bn_backward2(const void* da, const void* da2, const void* y, c
                                const float* save_mean, const float* save_rstd, const float* save_scale,
                                const float* save_shift, int64_t rows, int channels, int relu, void* dy,
                                void* dresidual, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                               void* stream);
+                               const void* relu_bits, void* stream);
+/* relu_bits: the bitmap written by the forward pass; when given, `act` is not read (may be NULL). */
 
 /* Max pooling, NHWC bf16, TF 'SAME' padding (out = ceil(in/stride), pad_before = pad_total/2).
  * Replaces tf.layers.max_pooling2d(pool_size=3, strides=2, padding='SAME'),

@@ -95,14 +95,14 @@ SIGNATURES = {
     'rigl_smallc_wgrad': (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _f32, _vp, _sz, _vp]),
     'rigl_bn_workspace_bytes': (_sz, [_i64, _i32]),
     'rigl_bn_forward_train': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _vp,
-                                        _vp, _vp, _vp, _vp, _sz, _vp]),
+                                        _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     'rigl_bn_forward_train_partials': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _f32, _i32, _vp, _vp,
-                                                 _vp, _vp, _vp, _vp, _vp, _vp]),
+                                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rigl_bn_apply': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'rigl_bn_backward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
                                    _vp, _sz, _vp]),
     'rigl_bn_backward2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
-                                    _vp, _sz, _vp]),
+                                    _vp, _sz, _vp, _vp]),
     'rigl_maxpool_same_forward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'rigl_maxpool_same_backward': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'rigl_set_force_simt': (C.c_int, [_i32]),

@@ -53,7 +53,7 @@ __device__ __forceinline__ void colsum_rows(
     const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ gout, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
     long long row0, long long row1, int C, float* __restrict__ partial_row /* [2][C] */,
-    float* red /* smem [rpi][vl][16] */) {
+    float* red /* smem [rpi][vl][16] */, const uint8_t* __restrict__ relu_bits = nullptr) {
   const int V = C >> 3;                         // 16-byte vectors per row
   const int vl = V < THREADS ? V : THREADS;
   const int rpi = THREADS / vl;              // rows handled per block iteration
@@ -74,6 +74,7 @@ __device__ __forceinline__ void colsum_rows(
       // 4 rows per trip: all loads are issued before any arithmetic (memory-level parallelism)
       for (long long rb = row0 + r_in; rb < row1; rb += 4ll * rpi) {
         uint4 qy[4], qd[4], qa[4], qe[4];
+        uint32_t qb[4];
         bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -84,7 +85,10 @@ __device__ __forceinline__ void colsum_rows(
             qy[u] = *reinterpret_cast<const uint4*>(y + off);
             if (MODE != 0) qd[u] = *reinterpret_cast<const uint4*>(da + off);
             if (MODE == 2) {
-              qa[u] = *reinterpret_cast<const uint4*>(act + off);
+              // ReLU mask of the block output: one BIT per element saved by the forward pass (1/16 of re-reading
+              // the bf16 output), or the output itself
+              if (relu_bits) qb[u] = relu_bits[off >> 3];
+              else qa[u] = *reinterpret_cast<const uint4*>(act + off);
               if (da2) qe[u] = *reinterpret_cast<const uint4*>(da2 + off);
             }
           }
@@ -108,10 +112,15 @@ __device__ __forceinline__ void colsum_rows(
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[i] = __bfloat162float(__float2bfloat16(g[i] + g2[i]));
               }
-              float fa[8];
-              unpack8(qa[u], fa);
+              if (relu_bits) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] = (!relu || fa[i] > 0.f) ? g[i] : 0.f;
+                for (int i = 0; i < 8; ++i) g[i] = (!relu || ((qb[u] >> i) & 1u)) ? g[i] : 0.f;
+              } else {
+                float fa[8];
+                unpack8(qa[u], fa);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = (!relu || fa[i] > 0.f) ? g[i] : 0.f;
+              }
               *reinterpret_cast<uint4*>(gout + off) = pack8(g);
             } else if (relu) {
 #pragma unroll
@@ -157,12 +166,12 @@ k_bn_colsum(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict
             const __nv_bfloat16* __restrict__ da2, const __nv_bfloat16* __restrict__ act,
             __nv_bfloat16* __restrict__ gout, const float* __restrict__ mean, const float* __restrict__ rstd,
             const float* __restrict__ scale, const float* __restrict__ shift, int relu, long long rows, int C,
-            long long rows_per_block, float* __restrict__ partial) {
+            long long rows_per_block, float* __restrict__ partial, const uint8_t* __restrict__ relu_bits) {
   extern __shared__ float red[];               // [rpi][V][16]
   const long long row0 = (long long)blockIdx.x * rows_per_block;
   const long long row1 = min(row0 + rows_per_block, rows);
   colsum_rows<MODE, kBnThreads>(y, da, da2, act, gout, mean, rstd, scale, shift, relu, row0, row1, C,
-                                partial + (size_t)blockIdx.x * 2 * C, red);
+                                partial + (size_t)blockIdx.x * 2 * C, red, relu_bits);
 }
 
 // Sums partial[b][which][c] over b for an 8-channel slab with 1024 threads: lane = (channel c = lane & 7,
@@ -261,7 +270,7 @@ __device__ __forceinline__ void load8f(const float* __restrict__ p, int v, float
 __global__ void __launch_bounds__(kBnThreads)
 k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
            const float* __restrict__ scale, const float* __restrict__ shift, int relu, long long nvec, int V,
-           __nv_bfloat16* __restrict__ out) {
+           __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ relu_bits) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool fixed_v = (stride % V) == 0;
@@ -284,6 +293,12 @@ k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
     }
     reinterpret_cast<uint4*>(out)[i] = pack8(f);
+    if (relu_bits) {                    // which outputs are positive: all the backward needs of this tensor
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m |= (f[k] > 0.f ? 1u : 0u) << k;
+      relu_bits[i] = (uint8_t)m;
+    }
   }
 }
 
@@ -402,7 +417,7 @@ k_bn_fwd_fused(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restr
                const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C,
                long long rows_per_block, float eps, float momentum, int relu, float* __restrict__ running_mean,
                float* __restrict__ running_var, float* mean, float* rstd, float* scale, float* shift,
-               __nv_bfloat16* __restrict__ out, float* partial, BnSync* sync) {
+               __nv_bfloat16* __restrict__ out, float* partial, BnSync* sync, uint8_t* __restrict__ relu_bits) {
   extern __shared__ float red[];
   __shared__ double sm_s[16][33], sm_q[16][33];
   const long long row0 = min((long long)blockIdx.x * rows_per_block, rows);
@@ -483,6 +498,12 @@ k_bn_fwd_fused(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restr
           for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
         }
         reinterpret_cast<uint4*>(out)[idx] = pack8(f);
+        if (relu_bits) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m |= (f[k] > 0.f ? 1u : 0u) << k;
+          relu_bits[idx] = (uint8_t)m;
+        }
       }
     }
   }
@@ -496,13 +517,14 @@ k_bn_bwd_fused(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __rest
                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
                const float* __restrict__ shift, long long rows, int C, long long rows_per_block, int relu,
                __nv_bfloat16* __restrict__ dy, __nv_bfloat16* gout, float* __restrict__ dgamma,
-               float* __restrict__ dbeta, float* partial, float* coef, BnSync* sync) {
+               float* __restrict__ dbeta, float* partial, float* coef, BnSync* sync,
+               const uint8_t* __restrict__ relu_bits) {
   extern __shared__ float red[];
   __shared__ double sm_s[16][33], sm_q[16][33];
   const long long row0 = min((long long)blockIdx.x * rows_per_block, rows);
   const long long row1 = min(row0 + rows_per_block, rows);
   colsum_rows<MODE, kFusedThreads>(y, da, da2, act, gout, mean, rstd, scale, shift, relu, row0, row1, C,
-                                   partial + (size_t)blockIdx.x * 2 * C, red);
+                                   partial + (size_t)blockIdx.x * 2 * C, red, relu_bits);
   grid_barrier(sync, gridDim.x);
   for (int slab = blockIdx.x; slab * 32 < C; slab += gridDim.x) {
     const int c = slab * 32 + (threadIdx.x & 31);
@@ -656,7 +678,7 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
                                      int64_t rows, int channels, float eps, float momentum, int relu,
                                      float* running_mean, float* running_var, float* save_mean, float* save_rstd,
                                      float* save_scale, float* save_shift, void* out, void* ws, size_t ws_bytes,
-                                     void* stream_) {
+                                     void* relu_bits, void* stream_) {
   RIGL_REQUIRE(y && gamma && beta && save_mean && save_rstd && save_scale && save_shift && out && ws,
                "rigl_bn_forward_train: null argument");
   RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, "rigl_bn_forward_train: channels must be a multiple of 8");
@@ -672,7 +694,7 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
       k_bn_fwd_fused<<<grid, kFusedThreads, fused_smem(channels), s>>>(
           (const __nv_bfloat16*)y, (const __nv_bfloat16*)residual, gamma, beta, rows, channels, frpb, eps, momentum, relu,
           running_mean, running_var, save_mean, save_rstd, save_scale, save_shift, (__nv_bfloat16*)out,
-          static_cast<float*>(ws), sync);
+          static_cast<float*>(ws), sync, static_cast<uint8_t*>(relu_bits));
       RIGL_LAUNCH_CHECK("k_bn_fwd_fused");
       return RIGL_OK;
     }
@@ -685,7 +707,7 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
   float* partial = static_cast<float*>(ws);
   k_bn_colsum<0><<<nb, kBnThreads, colsum_smem(channels), s>>>(
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, rows, channels,
-      rpb, partial);
+      rpb, partial, nullptr);
   RIGL_LAUNCH_CHECK("k_bn_colsum<0>");
   k_bn_finalize_fwd<<<(channels + kFinCh - 1) / kFinCh, 1024, 0, s>>>(partial, nb, channels, rows, eps, gamma, beta,
                                                                   save_mean, save_rstd, save_scale, save_shift,
@@ -696,7 +718,7 @@ extern "C" int rigl_bn_forward_train(const void* y, const void* residual, const 
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)residual,
                                                      save_scale, save_shift, relu, nvec, channels / 8,
-                                                     (__nv_bfloat16*)out);
+                                                     (__nv_bfloat16*)out, static_cast<uint8_t*>(relu_bits));
   RIGL_LAUNCH_CHECK("k_bn_apply");
   return RIGL_OK;
 }
@@ -708,7 +730,7 @@ extern "C" int rigl_bn_forward_train_partials(const void* y, const void* residua
                                               int64_t rows, int channels, float eps, float momentum, int relu,
                                               float* running_mean, float* running_var, float* save_mean,
                                               float* save_rstd, float* save_scale, float* save_shift, void* out,
-                                              void* stream_) {
+                                              void* relu_bits, void* stream_) {
   RIGL_REQUIRE(y && gamma && beta && partial && save_mean && save_rstd && save_scale && save_shift && out,
                "rigl_bn_forward_train_partials: null argument");
   RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0 && partial_rows > 0,
@@ -723,7 +745,7 @@ extern "C" int rigl_bn_forward_train_partials(const void* y, const void* residua
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, s>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)residual,
                                                      save_scale, save_shift, relu, nvec, channels / 8,
-                                                     (__nv_bfloat16*)out);
+                                                     (__nv_bfloat16*)out, static_cast<uint8_t*>(relu_bits));
   RIGL_LAUNCH_CHECK("k_bn_apply");
   return RIGL_OK;
 }
@@ -737,7 +759,7 @@ extern "C" int rigl_bn_apply(const void* y, const void* residual, const float* s
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_bn_apply<<<(unsigned)blocks, kBnThreads, 0, (cudaStream_t)stream_>>>(
       (const __nv_bfloat16*)y, (const __nv_bfloat16*)residual, scale, shift, relu, nvec, channels / 8,
-      (__nv_bfloat16*)out);
+      (__nv_bfloat16*)out, nullptr);
   RIGL_LAUNCH_CHECK("k_bn_apply");
   return RIGL_OK;
 }
@@ -747,20 +769,21 @@ extern "C" int rigl_bn_backward(const void* da, const void* y, const void* act, 
                                 int64_t rows, int channels, int relu, void* dy, void* dresidual, float* dgamma,
                                 float* dbeta, void* ws, size_t ws_bytes, void* stream_) {
   return rigl_bn_backward2(da, nullptr, y, act, save_mean, save_rstd, save_scale, save_shift, rows, channels, relu, dy,
-                           dresidual, dgamma, dbeta, ws, ws_bytes, stream_);
+                           dresidual, dgamma, dbeta, ws, ws_bytes, nullptr, stream_);
 }
 
 extern "C" int rigl_bn_backward2(const void* da, const void* da2, const void* y, const void* act,
                                  const float* save_mean, const float* save_rstd, const float* save_scale,
                                  const float* save_shift, int64_t rows, int channels, int relu, void* dy,
                                  void* dresidual, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                                 void* stream_) {
+                                 const void* relu_bits, void* stream_) {
   RIGL_REQUIRE(da2 == nullptr || (dresidual != nullptr && aligned16(da2)),
                "rigl_bn_backward2: a second output gradient needs the residual form (dresidual != NULL)");
   RIGL_REQUIRE(da && y && save_mean && save_rstd && save_scale && save_shift && dy && dgamma && dbeta && ws,
                "rigl_bn_backward: null argument");
   RIGL_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, "rigl_bn_backward: channels must be a multiple of 8");
-  RIGL_REQUIRE((dresidual == nullptr) || (act != nullptr), "rigl_bn_backward: the residual form needs the saved output");
+  RIGL_REQUIRE((dresidual == nullptr) || (act != nullptr) || (relu_bits != nullptr),
+               "rigl_bn_backward: the residual form needs the saved output or its ReLU bitmap");
   cudaStream_t s = (cudaStream_t)stream_;
   long long rpb;
   {
@@ -775,11 +798,12 @@ extern "C" int rigl_bn_backward2(const void* da, const void* da2, const void* y,
         k_bn_bwd_fused<2><<<grid, kFusedThreads, fused_smem(channels), s>>>(
             (const __nv_bfloat16*)da, (const __nv_bfloat16*)da2, (const __nv_bfloat16*)y, (const __nv_bfloat16*)act,
             save_mean, save_rstd, save_scale, save_shift, rows, channels, frpb, relu, (__nv_bfloat16*)dy,
-            (__nv_bfloat16*)dresidual, dgamma, dbeta, partial, coef, sync);
+            (__nv_bfloat16*)dresidual, dgamma, dbeta, partial, coef, sync, static_cast<const uint8_t*>(relu_bits));
       } else {
         k_bn_bwd_fused<1><<<grid, kFusedThreads, fused_smem(channels), s>>>(
             (const __nv_bfloat16*)da, nullptr, (const __nv_bfloat16*)y, nullptr, save_mean, save_rstd, save_scale,
-            save_shift, rows, channels, frpb, relu, (__nv_bfloat16*)dy, nullptr, dgamma, dbeta, partial, coef, sync);
+            save_shift, rows, channels, frpb, relu, (__nv_bfloat16*)dy, nullptr, dgamma, dbeta, partial, coef, sync,
+            nullptr);
       }
       RIGL_LAUNCH_CHECK("k_bn_bwd_fused");
       return RIGL_OK;
@@ -797,12 +821,13 @@ extern "C" int rigl_bn_backward2(const void* da, const void* da2, const void* y,
   if (residual_form) {
     k_bn_colsum<2><<<nb, kBnThreads, colsum_smem(channels), s>>>(
         (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, (const __nv_bfloat16*)da2, (const __nv_bfloat16*)act,
-        (__nv_bfloat16*)dresidual, save_mean, save_rstd, save_scale, save_shift, relu, rows, channels, rpb, partial);
+        (__nv_bfloat16*)dresidual, save_mean, save_rstd, save_scale, save_shift, relu, rows, channels, rpb, partial,
+        static_cast<const uint8_t*>(relu_bits));
     RIGL_LAUNCH_CHECK("k_bn_colsum<2>");
   } else {
     k_bn_colsum<1><<<nb, kBnThreads, colsum_smem(channels), s>>>(
         (const __nv_bfloat16*)y, (const __nv_bfloat16*)da, nullptr, nullptr, nullptr, save_mean, save_rstd, save_scale,
-        save_shift, relu, rows, channels, rpb, partial);
+        save_shift, relu, rows, channels, rpb, partial, nullptr);
     RIGL_LAUNCH_CHECK("k_bn_colsum<1>");
   }
   k_bn_finalize_bwd<<<(channels + kFinCh - 1) / kFinCh, 1024, 0, s>>>(partial, nb, channels, rows, save_mean, save_rstd,

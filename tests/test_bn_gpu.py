@@ -226,3 +226,37 @@ def test_conv_epilogue_bn_stats_only_where_profitable():
       assert (conv.bn_partial is not None) == expect, (cin, cout, k)
   finally:
     layers.FUSE_BN_STATS = old
+
+
+@pytest.mark.parametrize('shape', [(4, 8, 8, 64), (2, 7, 7, 2048), (16, 28, 28, 128), (64, 56, 56, 64), (3, 5, 9, 24)])
+@pytest.mark.parametrize('fork', [False, True])
+def test_bn_residual_backward_relu_bitmap_equals_rereading_the_output(shape, fork):
+  """Residual form: the forward apply writes one bit per element (output > 0) and the backward reads that bitmap
+  instead of the bf16 block output (norm.RELU_BITMASK, default).  Bit-identical to re-reading the output, on the
+  3-kernel and the single-launch paths, with one or two incoming gradients."""
+  from rigl_b200 import norm
+  n, h, w, c = shape
+  rng = np.random.RandomState(c * 3 + n)
+  y_np, r_np = rng.standard_normal(shape) * 1.3, rng.standard_normal(shape)
+  da_np, db_np = rng.standard_normal(shape), rng.standard_normal(shape)
+  res = []
+  old = norm.RELU_BITMASK
+  for use_bits in (True, False):
+    norm.RELU_BITMASK = use_bits
+    try:
+      bn = FusedBatchNormReLU(c, relu=True, device=DEV)
+      with torch.no_grad():
+        bn.weight.copy_(torch.linspace(0.5, 1.5, c))
+        bn.bias.copy_(torch.linspace(-0.3, 0.3, c))
+      y, r = _nhwc_to_dev(y_np).requires_grad_(True), _nhwc_to_dev(r_np).requires_grad_(True)
+      if fork:
+        a, b = bn(y, residual=r, fork=True)
+        torch.autograd.backward([a, b], [_nhwc_to_dev(da_np), _nhwc_to_dev(db_np)])
+      else:
+        a = bn(y, residual=r)
+        a.backward(_nhwc_to_dev(da_np))
+      res.append((a.detach().clone(), y.grad.clone(), r.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()))
+    finally:
+      norm.RELU_BITMASK = old
+  for got, want in zip(*res):
+    assert torch.equal(got, want)
