@@ -281,8 +281,7 @@ def run_ours(args):
     harness.step(images, labels)
   barrier()
   if rank != 0:
-    if dist is not None:
-      dist.destroy_process_group()
+    _teardown(dist, harness)
     return
   rec = Profiler.stop()
   per_kind = {}
@@ -349,8 +348,30 @@ def run_ours(args):
   if world == 1 and not args.no_cpu_baseline:
     out['cpu_baseline'] = cpu_baseline_leg(args.config, sample_batch=args.cpu_batch)
   _emit(out)
-  if dist is not None:
+  _teardown(dist, harness)
+
+
+def _teardown(dist, harness):
+  """NCCL refuses to finalise a communicator while CUDA graphs that captured its collectives are alive
+  (ncclCommDestroy waits for them): release the graphs first, then destroy the process group -- and never let a
+  stuck teardown turn a finished measurement into a hang."""
+  if dist is None:
+    return
+  import gc
+
+  def bail():
+    os._exit(0)
+  t = threading.Timer(45.0, bail)
+  t.daemon = True
+  t.start()
+  harness.release_cuda_graph()
+  gc.collect()
+  torch.cuda.synchronize()
+  try:
+    dist.barrier()
     dist.destroy_process_group()
+  finally:
+    t.cancel()
 
 
 def _cpu_port_timing(cfg_name, batch, steps, warmup):

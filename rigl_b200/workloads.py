@@ -315,6 +315,14 @@ class TrainHarness(object):
       ok = self._capture(warmup)
     return ok
 
+  def release_cuda_graph(self):
+    """Drops the captured graphs (back to the eager step).  Needed before torch.distributed is shut down: NCCL does
+    not finalise a communicator while graphs that captured its collectives exist."""
+    self.graphed = False
+    for name in ('_g_fb', '_g_opt', '_sloss'):
+      if hasattr(self, name):
+        setattr(self, name, None)
+
   def _capture(self, warmup):
     try:
       side = torch.cuda.Stream()
