@@ -177,6 +177,10 @@ def run_ours(args):
   cfg = CONFIGS[args.config]
   batch, image = cfg['batch'], cfg['image']
   dist, rank, world, local = _dist_setup(args.gpus)
+  if args.scaling == 'strong':               # fixed GLOBAL batch (the config's), split over the ranks
+    if batch % world:
+      raise SystemExit('--scaling strong: batch %d is not divisible by %d ranks' % (batch, world))
+    batch //= world
   dev = torch.device('cuda', local)
   torch.manual_seed(0)
   model = build_model(cfg, dev)
@@ -319,7 +323,7 @@ def run_ours(args):
   out = {
       'metric': cfg['metric'], 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+      'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
       'config': {'workload': cfg['workload'] + ', RigL drop 0.3 cosine every 100 steps, Nesterov momentum',
                  'name': args.config, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
                  'l2_policy': 'inputs larger than L2 (activations per step >> 126 MB)',
@@ -478,6 +482,9 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--layer-report', default=None)
   ap.add_argument('--no-graph', action='store_true', help='run the step eagerly (no CUDA-graph replay)')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='weak (default, the driver contract): the per-GPU batch is fixed; strong: the GLOBAL batch of '
+                       'the config is fixed and split over the ranks')
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'ours':
     args.warmup = 3
