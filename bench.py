@@ -325,7 +325,8 @@ def run_ours(args):
       'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True,
       'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
       'config': {'workload': cfg['workload'] + ', RigL drop 0.3 cosine every 100 steps, Nesterov momentum',
-                 'name': args.config, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
+                 'name': args.config, 'global_batch': batch * world, 'per_gpu_batch': batch,
+                 'parallelism': 'dp%d' % world,
                  'l2_policy': 'inputs larger than L2 (activations per step >> 126 MB)',
                  'mask_updates_in_timed_region': n_updates,
                  'masks_identical_across_replicas': masks_identical,
