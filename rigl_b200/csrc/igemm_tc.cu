@@ -941,7 +941,11 @@ static EncodeTiledFn g_encode = nullptr;
 static bool g_tma_store = true;     // RIGL_TMA_STORE=0 falls back to per-thread global stores
 static bool g_cta_pair = true;      // RIGL_CTA_PAIR=0: single-CTA MMA (M = 128) everywhere
 static bool g_pair_local = false;   // RIGL_PAIR_LOCALBAR=1: per-CTA full barriers + a forwarded arrive (measured 2.5x SLOWER than signalling the leader directly; kept as a documented negative result)
-static bool g_wgrad_fixup = true;        // RIGL_WGRAD_FIXUP=0: separate k_splitk_reduce launch per layer
+// RIGL_WGRAD_FIXUP=1: the last-arriving CTA of an output tile sums the split-K partials inside the wgrad kernel
+// instead of a separate k_splitk_reduce launch.  MEASURED SLOWER on ResNet-50 b256 (wgrad 4.3 -> 10.7 ms per step):
+// the layers with few output tiles run 100-300 splits, and one CTA then sums 20 MB that the separate kernel
+// spreads over the whole grid.  Kept opt-in as a documented negative result.
+static bool g_wgrad_fixup = false;
 static bool g_bn_stats_always = false;   // RIGL_BN_STATS_ALWAYS=1: epilogue statistics for every supported shape (tests)
 static bool g_halo = true;          // RIGL_HALO3X3=0: 3x3/s1 layers with <= 64 channels use the generic kernels
 static int g_halo_t = 0, g_halo_nbuf = 0;   // RIGL_HALO_CFG=T,NBUF: tuning override for the halo kernels
@@ -966,7 +970,7 @@ static void init_driver() {
   if (const char* e = getenv("RIGL_CTA_PAIR")) g_cta_pair = !(e[0] == '0');
   if (const char* e = getenv("RIGL_HALO3X3")) g_halo = !(e[0] == '0');
   if (const char* e = getenv("RIGL_BN_STATS_ALWAYS")) g_bn_stats_always = (e[0] == '1');
-  if (const char* e = getenv("RIGL_WGRAD_FIXUP")) g_wgrad_fixup = !(e[0] == '0');
+  if (const char* e = getenv("RIGL_WGRAD_FIXUP")) g_wgrad_fixup = (e[0] == '1');
   if (const char* e = getenv("RIGL_PAIR_LOCALBAR")) g_pair_local = (e[0] == '1');
   if (const char* e = getenv("RIGL_HALO_CFG")) sscanf(e, "%d,%d", &g_halo_t, &g_halo_nbuf);
   int dev = 0;
