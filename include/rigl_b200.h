@@ -344,6 +344,21 @@ RIGL_API int rigl_maxpool_same_forward(const void* x, int n, int h, int w, int c
 RIGL_API int rigl_maxpool_same_backward(const void* dy, const uint8_t* argmax, int n, int h, int w, int c,
                                         int ksize, int stride, void* dx, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Depthwise 3x3 convolution (stride 1 / 2, explicit padding 1), NHWC bf16, fp32 master weights [C][1][3][3]
+ * (flat index c*9 + kh*3 + kw), rounded to bf16 on load; fp32 accumulation.  Replaces
+ * depthwise_conv2d_fixed_padding of the reference's MobileNet-v1 (mobilenetv1_model.py:120-153; not a masked
+ * op there).  channels % 8 == 0.  x [n,h,w,c], y / dy [n,oh,ow,c] with oh = (h - 1)/stride + 1.
+ * ---------------------------------------------------------------------- */
+RIGL_API size_t rigl_depthwise3x3_workspace_bytes(int n, int h, int w, int c, int stride);
+RIGL_API int rigl_depthwise3x3_fprop(const void* x, const float* weights, int n, int h, int w, int c, int stride,
+                                     void* y, void* stream);
+RIGL_API int rigl_depthwise3x3_dgrad(const void* dy, const float* weights, int n, int h, int w, int c, int stride,
+                                     void* dx, void* stream);
+/* dw <- beta * dw + dL/dweights (fp32, deterministic order); beta in {0, 1}. */
+RIGL_API int rigl_depthwise3x3_wgrad(const void* x, const void* dy, int n, int h, int w, int c, int stride,
+                                     float* dw, float beta, void* ws, size_t ws_bytes, void* stream);
+
 /* 1 to route every conv call through the CUDA-core kernels (debug cross-check). */
 RIGL_API int rigl_set_force_simt(int on);
 

@@ -185,7 +185,7 @@ class MobileNetV1(nn.Module):
     blocks, cin = [], 32
     for i, (filters, stride) in enumerate(self.CFG):
       blk = nn.Module()
-      blk.depthwise = DenseConv2d(cin, cin, 3, stride=stride, padding=1, groups=cin, bias=False, device=device)
+      blk.depthwise = DepthwiseConv2d(cin, stride=stride, device=device)
       blk.bn_dw = _BNReLU(cin, device=device)
       blk.pointwise = SparseConv2d(cin, filters, 1, strides=1, padding='FIXED',
                                    name='resnet_model/contraction_1x1_%d' % i, device=device, registry=reg)
@@ -413,3 +413,59 @@ class TrainHarness(object):
     self.opt.collect_masked_grads()
     self.opt.apply_gradients(None, global_step=self.global_step)
     return loss
+
+
+class _DepthwiseFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, weight, stride):
+    from . import _cabi
+    n, c, h, w = x.shape
+    oh, ow = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((n, c, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    _cabi.check(_cabi.lib().rigl_depthwise3x3_fprop(x.data_ptr(), weight.data_ptr(), n, h, w, c, stride, y.data_ptr(),
+                                                    _cabi.stream_ptr()), 'rigl_depthwise3x3_fprop')
+    ctx.save_for_backward(x, weight)
+    ctx.stride = stride
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    from . import _cabi
+    from .layers import _workspace
+    x, weight = ctx.saved_tensors
+    n, c, h, w = x.shape
+    dy = dy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx = dw = None
+    if ctx.needs_input_grad[0]:
+      dx = torch.empty_like(x, memory_format=torch.channels_last)
+      _cabi.check(_cabi.lib().rigl_depthwise3x3_dgrad(dy.data_ptr(), weight.data_ptr(), n, h, w, c, ctx.stride,
+                                                      dx.data_ptr(), _cabi.stream_ptr()), 'rigl_depthwise3x3_dgrad')
+    if ctx.needs_input_grad[1]:
+      dw = torch.empty_like(weight)
+      ws = _workspace(x.device, _cabi.lib().rigl_depthwise3x3_workspace_bytes(n, h, w, c, ctx.stride))
+      _cabi.check(_cabi.lib().rigl_depthwise3x3_wgrad(x.data_ptr(), dy.data_ptr(), n, h, w, c, ctx.stride, dw.data_ptr(),
+                                                      0.0, ws.data_ptr(), ws.numel(), _cabi.stream_ptr()),
+                  'rigl_depthwise3x3_wgrad')
+    return dx, dw, None
+
+
+class DepthwiseConv2d(nn.Module):
+  """depthwise_conv2d_fixed_padding(kernel_size=3) of the reference's MobileNet-v1 (mobilenetv1_model.py:120-153):
+  dense (un-masked), fp32 master weights in the torch depthwise layout [C,1,3,3], bf16 compute on the streaming
+  kernels of csrc/depthwise.cu (RIGL_NATIVE_DEPTHWISE=0: stock cuDNN grouped conv)."""
+
+  def __init__(self, channels, stride=1, device='cuda'):
+    super(DepthwiseConv2d, self).__init__()
+    import math
+    import os
+    self.channels, self.stride = int(channels), int(stride)
+    self.weight = nn.Parameter(torch.empty(channels, 1, 3, 3, device=device))
+    nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+    self.native = os.environ.get('RIGL_NATIVE_DEPTHWISE', '1') != '0'
+
+  def forward(self, x):
+    if self.native and x.is_cuda and self.channels % 8 == 0:
+      x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+      return _DepthwiseFn.apply(x, self.weight, self.stride)
+    return F.conv2d(x, self.weight.to(torch.bfloat16), None, self.stride, 1, 1, self.channels)

@@ -383,3 +383,30 @@ def test_conv_wgrad_accumulates_over_backward_passes():
   once = layer.masked_weights.dense_grad.clone()
   layer(x).backward(dy)                       # fresh is still True: accumulates
   assert torch.allclose(layer.masked_weights.dense_grad, once + once, rtol=1e-5, atol=1e-5 * float(once.abs().max()))
+
+
+@pytest.mark.parametrize('case', [(2, 16, 16, 32, 1), (2, 17, 13, 64, 2), (3, 14, 14, 256, 1), (2, 8, 8, 1024, 2),
+                                  (4, 112, 112, 32, 1), (2, 56, 56, 128, 2), (1, 5, 7, 24, 1)])
+def test_depthwise3x3_vs_fp64(case):
+  """Native depthwise 3x3 (csrc/depthwise.cu; MobileNet-v1's depthwise_conv2d_fixed_padding, mobilenetv1_model.py:
+  120-153) forward, input gradient and weight gradient against a float64 grouped convolution on the same
+  bf16-rounded operands."""
+  from rigl_b200.workloads import DepthwiseConv2d
+  n, h, w, c, stride = case
+  torch.manual_seed(c + h)
+  dw = DepthwiseConv2d(c, stride=stride, device=DEV)
+  with torch.no_grad():
+    dw.weight.copy_(dw.weight.to(torch.bfloat16).float() * 3)
+    dw.weight.copy_(dw.weight.to(torch.bfloat16).float())
+  x = torch.randn(n, c, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+  y = dw(x)
+  x64 = x.detach().double().cpu().requires_grad_(True)
+  w64 = dw.weight.detach().double().cpu().requires_grad_(True)
+  y64 = torch.nn.functional.conv2d(x64, w64, None, stride, 1, 1, c)
+  assert tuple(y.shape) == tuple(y64.shape)
+  dy = torch.randn_like(y64).to(torch.bfloat16)
+  y.backward(dy.to(DEV).contiguous(memory_format=torch.channels_last))
+  y64.backward(dy.double())
+  _check_bf16(y.permute(0, 2, 3, 1), y64.detach().permute(0, 2, 3, 1).numpy(), 'depthwise fprop %s' % (case,))
+  _check_bf16(x.grad.permute(0, 2, 3, 1), x64.grad.permute(0, 2, 3, 1).numpy(), 'depthwise dgrad %s' % (case,))
+  _check_f32(dw.weight.grad, w64.grad.numpy(), 'depthwise wgrad %s' % (case,))

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${NG:-2}
+run() { tag=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2k_${tag}_n$N.json 2> gpurun_out/r2k_${tag}_n$N.err; echo "$tag exit $?"; python -c "
+import json; d=json.load(open('gpurun_out/r2k_${tag}_n$N.json')); print('$tag', d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['masks_identical_across_replicas'], d['config']['cuda_graph'])" || tail -15 gpurun_out/r2k_${tag}_n$N.err; }
+/usr/bin/time -v true 2>/dev/null
+s=$(date +%s); run overlap RIGL_DP_OVERLAP=1; echo "wall $(( $(date +%s) - s )) s"
+s=$(date +%s); run blocking RIGL_DP_OVERLAP=0; echo "wall $(( $(date +%s) - s )) s"
