@@ -96,7 +96,12 @@ class ClockSampler(object):
     for line in self.proc.stdout:
       self.rows.append([c.strip() for c in line.split(',')])
 
+  def mark(self):
+    """Samples taken so far (while nvidia-smi was starting up, before the timed region) are dropped."""
+    self.skip = len(self.rows)
+
   def stop(self):
+    self.rows = self.rows[getattr(self, 'skip', 0):]
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     self.proc.terminate()
@@ -208,23 +213,37 @@ def run_ours(args):
   graphed = False
   if not args.no_graph:
     graphed = harness.enable_cuda_graph(images, labels)
+  # nvidia-smi is started BEFORE the warm-up: its start-up initialises NVML on every GPU of the box, which stalls
+  # them for tens of milliseconds (measured at N = 8) -- that belongs to no step; it then samples every 200 ms
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  # warm-up of the UPDATE path too: the first update after the momentum slots exist rebuilds the launch plan
+  # (device allocations), like a first step does; the timed updates then run the steady-state path
+  harness.opt.collect_masked_grads()
+  harness.opt.drop_fraction = np.float32(0.3)
+  harness.opt.mask_update_op()
   for _ in range(args.warmup):
     harness.step(images, labels)
   # align the schedule: the next update is due in the middle of the timed region (then every 100 steps)
   harness.opt._last_update_step = harness.global_step.value + min(args.steps, UPDATE_EVERY) // 2 - UPDATE_EVERY
   barrier()
-  sampler = ClockSampler(local)
-  if rank == 0:
-    sampler.start()
+  sampler.mark()
   launches0 = _cabi.launch_count() + getattr(harness, 'replayed_kernel_launches', 0)
   start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
   start.record()
-  n_updates = 0
-  for _ in range(args.steps):
+  marks[0].record()
+  n_updates, update_steps = 0, []
+  for i in range(args.steps):
     harness.step(images, labels)
-    n_updates += int(harness.opt.last_update_was_mask_update)
+    marks[i + 1].record()
+    if harness.opt.last_update_was_mask_update:
+      n_updates += 1
+      update_steps.append(i)
   stop.record()
   barrier()
+  per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
   clocks = sampler.stop() if rank == 0 else None
   launches = _cabi.launch_count() + getattr(harness, 'replayed_kernel_launches', 0) - launches0
   ms = torch.tensor([start.elapsed_time(stop)], device=dev, dtype=torch.float64)
@@ -328,7 +347,10 @@ def run_ours(args):
                  'name': args.config, 'global_batch': batch * world, 'per_gpu_batch': batch,
                  'parallelism': 'dp%d' % world,
                  'l2_policy': 'inputs larger than L2 (activations per step >> 126 MB)',
-                 'mask_updates_in_timed_region': n_updates,
+                 'mask_updates_in_timed_region': n_updates, 'mask_update_steps': update_steps,
+                 'step_ms': {'p50': float(np.median(per_step)), 'p90': float(np.percentile(per_step, 90)),
+                             'max': float(max(per_step)), 'argmax': int(np.argmax(per_step)),
+                             'note': 'rank 0, per step, device events'},
                  'masks_identical_across_replicas': masks_identical,
                  'cuda_graph': bool(graphed)},
       'clocks': clocks,
