@@ -60,41 +60,62 @@ k_depthwise3x3(DwGeom g, const __nv_bfloat16* __restrict__ src, const float* __r
   const int col = blockIdx.x * blockDim.y + threadIdx.y, n = blockIdx.z;
   if (col >= out_w) return;
   const int row_end = min(out_h, (int)(blockIdx.y + 1) * kDwRows);
+  const bool s2 = g.s == 2;
   for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float wt[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t) dw_load_w(w, v, t, wt[t]);
+    // column taps: source column and validity do not depend on the row
+    int wi[3];
+    bool wok[3];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      if (!FLIP) {
+        wi[kw] = col * g.s + kw - 1;
+        wok[kw] = wi[kw] >= 0 && wi[kw] < in_w;
+      } else {
+        const int t = col + 1 - kw;
+        wok[kw] = t >= 0 && (!s2 || (t & 1) == 0);
+        wi[kw] = s2 ? (t >> 1) : t;
+        wok[kw] = wok[kw] && wi[kw] < in_w;
+      }
+      if (!wok[kw]) wi[kw] = 0;                       // clamped: the load stays in bounds, the value is dropped
+    }
+    const __nv_bfloat16* base = src + (long long)n * in_h * in_w * g.c + 8 * v;
     for (int row = blockIdx.y * kDwRows; row < row_end; ++row) {
+      // all nine loads are issued before any arithmetic (no control flow between them: memory-level parallelism)
+      uint4 q[9];
+      bool ok[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int hi;
+        bool hok;
+        if (!FLIP) {
+          hi = row * g.s + kh - 1;
+          hok = hi >= 0 && hi < in_h;
+        } else {
+          const int t = row + 1 - kh;
+          hok = t >= 0 && (!s2 || (t & 1) == 0);
+          hi = s2 ? (t >> 1) : t;
+          hok = hok && hi < in_h;
+        }
+        if (!hok) hi = 0;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          ok[kh * 3 + kw] = hok && wok[kw];
+          q[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(base + ((long long)hi * in_w + wi[kw]) * g.c));
+        }
+      }
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        int hi;
-        if (!FLIP) {
-          hi = row * g.s + kh - 1;
-        } else {
-          const int t = row + 1 - kh;
-          if (t < 0 || (t % g.s) != 0) continue;
-          hi = t / g.s;
-        }
-        if (hi < 0 || hi >= in_h) continue;
+      for (int t = 0; t < 9; ++t) {
+        float xs[8];
+        dw_unpack8(q[t], xs);
+        const float m = ok[t] ? 1.f : 0.f;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          int wi;
-          if (!FLIP) {
-            wi = col * g.s + kw - 1;
-          } else {
-            const int t = col + 1 - kw;
-            if (t < 0 || (t % g.s) != 0) continue;
-            wi = t / g.s;
-          }
-          if (wi < 0 || wi >= in_w) continue;
-          float xs[8];
-          dw_unpack8(*reinterpret_cast<const uint4*>(src + (((long long)n * in_h + hi) * in_w + wi) * g.c + 8 * v), xs);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(xs[e], wt[kh * 3 + kw][e], acc[e]);
-        }
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xs[e] * m, wt[t][e], acc[e]);
       }
       *reinterpret_cast<uint4*>(dst + (((long long)n * out_h + row) * out_w + col) * g.c + 8 * v) = dw_pack8(acc);
     }
@@ -126,21 +147,32 @@ k_depthwise3x3_wgrad(DwGeom g, const __nv_bfloat16* __restrict__ x, const __nv_b
     for (long long r = r0; r < r1; ++r) {
       const int n = (int)(r / g.oh), oh = (int)(r % g.oh);
       for (int ow = lane_c; ow < g.ow; ow += kDwCols) {
-        float d[8];
-        dw_unpack8(*reinterpret_cast<const uint4*>(dy + (((long long)n * g.oh + oh) * g.ow + ow) * g.c + 8 * v), d);
+        uint4 q[9];
+        bool ok[9];
+        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * g.oh + oh) * g.ow + ow) * g.c + 8 * v));
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          const int hi = oh * g.s + kh - 1;
-          if (hi < 0 || hi >= g.h) continue;
+          int hi = oh * g.s + kh - 1;
+          const bool hok = hi >= 0 && hi < g.h;
+          if (!hok) hi = 0;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const int wi = ow * g.s + kw - 1;
-            if (wi < 0 || wi >= g.w) continue;
-            float xs[8];
-            dw_unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * g.h + hi) * g.w + wi) * g.c + 8 * v), xs);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[kh * 3 + kw][e] = fmaf(xs[e], d[e], acc[kh * 3 + kw][e]);
+            int wi = ow * g.s + kw - 1;
+            const bool wok = wi >= 0 && wi < g.w;
+            if (!wok) wi = 0;
+            ok[kh * 3 + kw] = hok && wok;
+            q[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * g.h + hi) * g.w + wi) * g.c + 8 * v));
           }
+        }
+        float d[8];
+        dw_unpack8(qd, d);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          float xs[8];
+          dw_unpack8(q[t], xs);
+          const float m = ok[t] ? 1.f : 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(xs[e] * m, d[e], acc[t][e]);
         }
       }
     }

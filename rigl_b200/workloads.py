@@ -453,7 +453,8 @@ class _DepthwiseFn(torch.autograd.Function):
 class DepthwiseConv2d(nn.Module):
   """depthwise_conv2d_fixed_padding(kernel_size=3) of the reference's MobileNet-v1 (mobilenetv1_model.py:120-153):
   dense (un-masked), fp32 master weights in the torch depthwise layout [C,1,3,3], bf16 compute on the streaming
-  kernels of csrc/depthwise.cu (RIGL_NATIVE_DEPTHWISE=0: stock cuDNN grouped conv)."""
+  kernels of csrc/depthwise.cu when RIGL_NATIVE_DEPTHWISE=1; default: the stock cuDNN grouped conv, which was
+  the faster of the two on B200 when measured."""
 
   def __init__(self, channels, stride=1, device='cuda'):
     super(DepthwiseConv2d, self).__init__()
@@ -462,7 +463,7 @@ class DepthwiseConv2d(nn.Module):
     self.channels, self.stride = int(channels), int(stride)
     self.weight = nn.Parameter(torch.empty(channels, 1, 3, 3, device=device))
     nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
-    self.native = os.environ.get('RIGL_NATIVE_DEPTHWISE', '1') != '0'
+    self.native = os.environ.get('RIGL_NATIVE_DEPTHWISE', '0') == '1'
 
   def forward(self, x):
     if self.native and x.is_cuda and self.channels % 8 == 0:

@@ -395,6 +395,7 @@ def test_depthwise3x3_vs_fp64(case):
   n, h, w, c, stride = case
   torch.manual_seed(c + h)
   dw = DepthwiseConv2d(c, stride=stride, device=DEV)
+  dw.native = True                       # the csrc/depthwise.cu kernels (the default path is cuDNN)
   with torch.no_grad():
     dw.weight.copy_(dw.weight.to(torch.bfloat16).float() * 3)
     dw.weight.copy_(dw.weight.to(torch.bfloat16).float())
