@@ -116,7 +116,7 @@ class MaskUpdateEngine(object):
 
   @staticmethod
   def _layer_key(ly):
-    slots = list(ly.get('slots') or [])
+    slots = list(ly.get('slots') or [])[:2]
     return (ly['weights'].data_ptr(), ly['score_grow'].data_ptr(), ly['mask'].bits.data_ptr(),
             _ptr(ly.get('noise')), tuple(s.data_ptr() for s in slots), _ptr(ly.get('grow_values')),
             _ptr(ly.get('score_drop')), int(ly['mask'].size), int(ly.get('n_prune', -1)),
@@ -136,9 +136,7 @@ class MaskUpdateEngine(object):
           if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or not t.is_cuda:
             raise ValueError('%s of %s must be a contiguous float32 CUDA tensor of %d elements'
                              % (name, ly['mask'].name, n))
-      slots = list(ly.get('slots') or [])
-      if len(slots) > 2:
-        raise ValueError('at most 2 optimizer slots per weight are supported')
+      slots = list(ly.get('slots') or [])[:2]        # slots beyond two are reset on the host side (see run)
       d.weights = ly['weights'].data_ptr()
       d.score_grow = ly['score_grow'].data_ptr()
       d.mask_bits = ly['mask'].bits.data_ptr()
@@ -172,6 +170,31 @@ class MaskUpdateEngine(object):
     if plan_key is None or plan_key != getattr(self, '_caller_key', None) or not (self._plan and self._plan.value):
       self.prepare(layers)
       self._caller_key = plan_key
+    # The kernels reset up to two optimizer slots per weight in place (SGD momentum; Adam's two moments).  Further
+    # slots (amsgrad's max_exp_avg_sq, LAMB ...) are reset after the update from the bitmaps: new connections =
+    # new mask & ~old mask (base.py:332-333, 345-353, 555-564 reset EVERY slot).
+    extra = [(ly, list(ly['slots'])[2:], ly['mask'].bits.clone()) for ly in layers if len(ly.get('slots') or []) > 2]
+    if extra and reinit_when_same:
+      raise ValueError('reinit_when_same with more than 2 optimizer slots per weight is not supported')
+    self._launch(drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std, noise_seed)
+    for ly, slots, old_bits in extra:
+      n = ly['mask'].size
+      grown_bits = ly['mask'].bits & ~old_bits
+      grown = torch.empty(n, dtype=torch.float32, device=grown_bits.device)
+      _cabi.check(_cabi.lib().rigl_mask_unpack_f32(grown_bits.data_ptr(), n, grown.data_ptr(), _cabi.stream_ptr()),
+                  'rigl_mask_unpack_f32')
+      grown = grown > 0
+      g = ly.get('grad')
+      g = ly['score_grow'] if g is None else g
+      value = (g * float(acc_scale)) if acc_scale else None
+      for sl in slots:
+        flat = sl.view(-1)
+        if value is None:
+          flat.masked_fill_(grown, 0.)
+        else:
+          flat.copy_(torch.where(grown, value, flat))
+
+  def _launch(self, drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std, noise_seed):
     if noise_std:
       # drop-score noise drawn in-kernel for the layers without a `noise` tensor (keyed by noise_seed and each
       # layer's `noise_key`; rigl_mask_noise_fill reproduces it)

@@ -362,3 +362,13 @@ def test_in_kernel_noise_equals_materialised_noise():
     # and the noise really changed the outcome relative to a noiseless update
   quiet = orc.rigl_mask_update(layers[1]['mask'], layers[1]['w'], layers[1]['g'], np.float32(0.3))
   assert not np.array_equal(quiet['mask'], specs[1]['mask'].numpy())
+
+
+@pytest.mark.parametrize('acc_scale', [0.0, 0.5])
+def test_three_optimizer_slots(acc_scale):
+  """The reference resets EVERY optimizer slot at new connections (base.py:345-353, 555-564).  The kernels carry
+  two slot pointers per layer (momentum; Adam's moments); a third one (amsgrad's max_exp_avg_sq) is reset from the
+  old / new bitmaps after the update -- bit-identical to the oracle."""
+  rng = np.random.RandomState(17)
+  layers = [_layer(rng, (300, 100), 0.8, slots=3), _layer(rng, (3, 3, 16, 32), 0.6, slots=3)]
+  _run_case(layers, 0.3, acc_scale=acc_scale)
