@@ -186,13 +186,10 @@ class MaskUpdateEngine(object):
       grown = grown > 0
       g = ly.get('grad')
       g = ly['score_grow'] if g is None else g
-      value = (g * float(acc_scale)) if acc_scale else None
-      for sl in slots:
+      value = g * float(acc_scale)        # (always the product: acc_scale = 0 gives the SIGNED zeros the kernels and
+      for sl in slots:                    #  the reference's `masked_grad * initial_acc_scale` give)
         flat = sl.view(-1)
-        if value is None:
-          flat.masked_fill_(grown, 0.)
-        else:
-          flat.copy_(torch.where(grown, value, flat))
+        flat.copy_(torch.where(grown, value, flat))
 
   def _launch(self, drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std, noise_seed):
     if noise_std:
