@@ -266,8 +266,12 @@ class TrainHarness(object):
                              use_tpu=data_parallel is not None).bind(model.registry)
     self.global_step = GlobalStep(0)
     self.dp = data_parallel
-    # RIGL_DP_OVERLAP=0: one blocking all-reduce after backward instead of the bucketed, overlapped exchange
-    self._dp_overlap = os.environ.get('RIGL_DP_OVERLAP', '1') != '0'
+    # Gradient exchange under data parallelism.  Default: ONE all-reduce of the flat buffer between the two graph
+    # replays (backward; optimizer).  RIGL_DP_OVERLAP=1: bucketed all-reduces launched from inside backward on a
+    # communication stream and captured with the step.  Measured on 8 x B200 (profiles/r02_bench_n8*.json): 22.12 vs
+    # 22.21 ms per step (N = 1: 21.6) -- the 102 MB exchange takes ~0.4 ms over NVSwitch, and hiding it costs as
+    # much in SM contention as it saves, so the simpler form is the default.
+    self._dp_overlap = os.environ.get('RIGL_DP_OVERLAP', '0') == '1'
     self._pack_ahead = on_cuda and os.environ.get('RIGL_PACK_AHEAD', '1') != '0'
     if self.dp is not None:
       self.dp.attach(model)
