@@ -92,6 +92,64 @@ k_maxpool_bwd(PoolGeom g, const __nv_bfloat16* __restrict__ dy, const uint8_t* _
   }
 }
 
+// The stem's case (3x3 window, stride 2, no leading pad, even extents): a 2x2 quad of input pixels is covered by the
+// same four windows (oh-1|oh) x (ow-1|ow), nine (pixel, window) visits in all.  One thread = one quad x 8 channels:
+// it loads the four outputs once (2.25 -> 1 window loads per input pixel) and writes the four pixels as two 32-byte
+// runs.  Same accumulation order as the generic gather (oh ascending, then ow): bit-identical results.
+__global__ void __launch_bounds__(256)
+k_maxpool_bwd_3x3s2(PoolGeom g, const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                    __nv_bfloat16* __restrict__ dx) {
+  const int V = g.c >> 3;
+  const int qw = blockIdx.x * blockDim.y + threadIdx.y, qh = blockIdx.y, n = blockIdx.z;
+  if (qw >= (g.w >> 1)) return;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float acc[4][8];            // pixels (0,0) (0,1) (1,0) (1,1) of the quad
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[p][e] = 0.f;
+    uint2 a[4];
+    uint4 d[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {           // windows in the generic kernel's visiting order
+      const int oh = qh - 1 + (j >> 1), ow = qw - 1 + (j & 1);
+      ok[j] = oh >= 0 && ow >= 0 && oh < g.oh && ow < g.ow;
+      a[j] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      d[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[j]) {
+        const long long p = (((long long)n * g.oh + oh) * g.ow + ow) * g.c + 8 * v;
+        a[j] = *reinterpret_cast<const uint2*>(idx + p);
+        d[j] = *reinterpret_cast<const uint4*>(dy + p);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16* dv = reinterpret_cast<const __nv_bfloat16*>(&d[j]);
+      const int dh = 2 - 2 * (j >> 1), dw = 2 - 2 * (j & 1);   // window-relative position of pixel (0,0)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ai = (int)(((e < 4 ? a[j].x : a[j].y) >> (8 * (e & 3))) & 0xFFu);
+        const float f = __bfloat162float(dv[e]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int rh = dh + (p >> 1), rw = dw + (p & 1);
+          if (rh < 3 && rw < 3 && ai == rh * 3 + rw) acc[p][e] += f;
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      uint4 o;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(acc[p][2 * e], acc[p][2 * e + 1]);
+      const long long q = ((long long)n * g.h + 2 * qh + (p >> 1)) * g.w + 2 * qw + (p & 1);
+      *reinterpret_cast<uint4*>(dx + q * g.c + 8 * v) = o;
+    }
+  }
+}
+
 static int pool_geom(int n, int h, int w, int c, int k, int s, PoolGeom* g) {
   RIGL_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && k > 0 && s > 0 && k * k <= 255,
                "maxpool: bad geometry (channels must be a multiple of 8)");
@@ -126,6 +184,13 @@ extern "C" int rigl_maxpool_same_backward(const void* dy, const uint8_t* argmax,
   if (rc != RIGL_OK) return rc;
   RIGL_REQUIRE(dy && dx && argmax, "rigl_maxpool_same_backward: null tensor");
   RIGL_REQUIRE(g.h <= 65535 && n <= 65535, "rigl_maxpool_same_backward: extent too large");
+  if (g.k == 3 && g.s == 2 && g.pad == 0 && (g.h & 1) == 0 && (g.w & 1) == 0) {
+    const dim3 block(8, 32), grid((unsigned)((g.w / 2 + 31) / 32), (unsigned)(g.h / 2), (unsigned)n);
+    k_maxpool_bwd_3x3s2<<<grid, block, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)dy, argmax,
+                                                                   (__nv_bfloat16*)dx);
+    RIGL_LAUNCH_CHECK("k_maxpool_bwd_3x3s2");
+    return RIGL_OK;
+  }
   const dim3 block(8, 32), grid((unsigned)((g.w + 31) / 32), (unsigned)g.h, (unsigned)n);
   k_maxpool_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx);
   RIGL_LAUNCH_CHECK("k_maxpool_bwd");
