@@ -41,7 +41,7 @@ constexpr int kBinShift = 20;
 constexpr uint32_t kKeyZero = 0x80000000u;  // ord_key(+0.0f)
 constexpr int kScanThreads = 256;
 constexpr int kGroup = 128;                 // elements per warp-iteration (float4 per lane)
-constexpr int kChunk = 32768;               // elements per block
+constexpr int kChunk = 32768;               // default elements per scan block (plan->chunk; RIGL_MASK_CHUNK)
 constexpr int kResolveThreads = 1024;
 constexpr int kRBins = 2048;
 constexpr int kBatch = 2;                   // groups whose loads are issued together per trip
@@ -96,6 +96,7 @@ struct RunParams {
   int force_wlo;              // >= 0: test knob, overrides the sampled lower bound of the grow histogram
   uint64_t off_task_cnt;      // workspace offset of the per-block candidate counts: [2][n_blocks] (drop, grow)
   uint32_t n_blocks;
+  uint32_t chunk;             // elements per scan block (a multiple of 4096)
 };
 
 // Counter-based N(0,1) noise for the drop scores (generic_mask_update's `noise_std`, base.py:260-274, 523-538):
@@ -204,7 +205,7 @@ k_hist_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const bool all_active = (L.flags & RIGL_LAYER_ALL_ACTIVE) != 0;     // rank every position (mask treated as ones)
   uint32_t zero_cnt = 0, ones = 0;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kTrips = kChunk / kGroup / kWarps;      // 32 groups per warp
+  const int kTrips = (int)prm.chunk / kGroup / kWarps;    // groups per warp
 #pragma unroll 1
   for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
     // issue the loads of 4 groups before touching any of them (memory-level parallelism)
@@ -315,7 +316,7 @@ __device__ __forceinline__ void find_bin_desc(const uint32_t* hist, uint32_t nee
 // ----------------------------------------------------------------------------
 // B: per-layer counts and drop threshold bin
 // ----------------------------------------------------------------------------
-constexpr uint32_t kSampleMinN = 4 * kChunk;   // smaller layers fill the whole grow histogram (cheap anyway)
+constexpr uint32_t kSampleMinN = 131072;   // smaller layers fill the whole grow histogram (cheap anyway)
 constexpr int kSamplesPerThread = 4;           // 4096 sampled positions per layer
 
 template <bool kV3>
@@ -403,6 +404,33 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   if (threadIdx.x == 0) st->grow_wlo = wlo;
 }
 
+// Appends one warp's candidates of a 128-element group to a candidate list: lane holds up to four (bit c of nibc set
+// <=> element e0 + c, key keys[c]).  One warp scan + ONE counter atomic per group (instead of a ballot, an atomic and a
+// shuffle per element column); the order inside the list is irrelevant to the selection.
+template <bool kShared>
+__device__ __forceinline__ void append_cands(uint32_t nibc, const uint32_t (&keys)[4], uint32_t e0, int lane,
+                                             uint2* __restrict__ cand, uint32_t* counter, uint32_t* __restrict__ hist2) {
+  if (!__any_sync(0xffffffffu, nibc != 0u)) return;
+  const uint32_t mine = __popc(nibc);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  uint32_t base = 0;
+  if (lane == 31) base = atomicAdd(counter, incl);     // shared-memory (block-private list) or global (layer list)
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t pos = base + incl - mine;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if ((nibc >> c) & 1u) {
+      cand[pos++] = make_uint2(keys[c], e0 + c);
+      atomicAdd(&hist2[(keys[c] >> 8) & 0xFFFu], 1u);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // C: classify against the drop threshold bin, build mask1, grow histogram
 // ----------------------------------------------------------------------------
@@ -436,7 +464,7 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const bool all_active = (L.flags & RIGL_LAYER_ALL_ACTIVE) != 0;
   uint32_t zero_cnt = 0;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kTrips = kChunk / kGroup / kWarps;
+  const int kTrips = (int)prm.chunk / kGroup / kWarps;
 #pragma unroll 1
   for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
     float4 wv[kBatch], gv[kBatch], nv[kBatch];
@@ -464,7 +492,8 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       const float ws4[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
       const float gs4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
       const float ns4[4] = {nv[u].x, nv[u].y, nv[u].z, nv[u].w};
-      uint32_t nib1 = 0;
+      uint32_t nib1 = 0, nibc = 0;
+      uint32_t keys[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const bool valid = e0 + c < n;
@@ -473,27 +502,18 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
           key = ord_key(drop_score(ws4[c], (nib >> c) & 1u, ns4[c], has_noise, explicit_score));
           bin = key >> kBinShift;
         }
+        keys[c] = key;
         const bool is_cand = valid && bin == bucket;
         const bool kept = valid && bin > bucket;
         if (kept) nib1 |= 1u << c;
-        const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
-        if (cm) {
-          uint32_t pos = 0;
-          const int leader = __ffs(cm) - 1;
-          if (lane == leader)
-            pos = kV3 ? atomicAdd(&s_cand, (uint32_t)__popc(cm)) : atomicAdd(&st->cand_cnt_drop, (uint32_t)__popc(cm));
-          pos = __shfl_sync(0xffffffffu, pos, leader);
-          if (is_cand) {
-            cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
-            atomicAdd(&hist2[(key >> 8) & 0xFFFu], 1u);
-          }
-        }
+        if (is_cand) nibc |= 1u << c;
         if (valid && !kept && !is_cand) {          // definitely dropped / inactive: a grow contender
           const uint32_t gkey = grow_key(gs4[c], grow_signed);
           if (gkey == kKeyZero) ++zero_cnt;
           else if (!kV3 || (gkey >> kBinShift) >= wlo) atomicAdd(&hist[gkey >> kBinShift], 1u);
         }
       }
+      append_cands<kV3>(nibc, keys, e0, lane, cand, kV3 ? &s_cand : &st->cand_cnt_drop, hist2);
       const uint32_t word = combine_nibbles(nib1, lane);
       if ((lane & 7) == 0) mask1[(bases[u] >> 5) + (lane >> 3)] = word;
     }
@@ -544,14 +564,15 @@ constexpr int kSubCap = 1024;      // sub-candidates ranked exactly in shared me
 // scan block (blk_cnt[b] entries at cand + b * kChunk): a warp per list, lanes striding over it.
 template <bool kV3, typename F>
 __device__ __forceinline__ void for_each_cand(const uint2* __restrict__ cand, uint32_t cnt,
-                                              const uint32_t* __restrict__ blk_cnt, uint32_t n_lists, F&& f) {
+                                              const uint32_t* __restrict__ blk_cnt, uint32_t n_lists, uint32_t chunk,
+                                              F&& f) {
   if (!kV3) {
     for (uint32_t i = threadIdx.x; i < cnt; i += kResolveThreads) f(cand[i]);
   } else {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t b = warp; b < n_lists; b += kResolveThreads / 32) {
       const uint32_t c = __ldcg(blk_cnt + b);
-      const uint2* lst = cand + (size_t)b * kChunk;
+      const uint2* lst = cand + (size_t)b * chunk;
       for (uint32_t i = lane; i < c; i += 32) f(lst[i]);
     }
   }
@@ -600,7 +621,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     thresh = (uint64_t)b2 << 40;
     if (in_bin != need) {
       // gather the elements of the level-2 threshold bin
-      for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, [&](const uint2 c) {
+      for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
         if (((c.x >> 8) & 0xFFFu) == b2) {
           const uint32_t pos = atomicAdd(&sub_cnt, 1u);
           if (pos < (uint32_t)kSubCap) sub[pos] = c;
@@ -628,7 +649,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
           const int sh = shifts[p], wd = widths[p];
           for (int b = tid; b < kRBins; b += kResolveThreads) h2[b] = 0;
           __syncthreads();
-          for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, [&](const uint2 cc) {
+          for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 cc) {
             const uint64_t c = composite(cc);
             if ((c >> (sh + wd)) == prefix) atomicAdd(&h2[(uint32_t)(c >> sh) & ((1u << wd) - 1u)], 1u);
           });
@@ -652,7 +673,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     if (tid == 0) { st->grow_thresh_lo = (uint32_t)thresh; st->grow_thresh_hi = (uint32_t)(thresh >> 32); }
     return;
   }
-  for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, [&](const uint2 c) {
+  for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
     const bool sel = composite(c) >= thresh;
     const uint32_t e = c.y;
     if (sel) {
@@ -737,7 +758,7 @@ k_publish_mask(const LayerDev* __restrict__ layers, const BlockTask* __restrict_
   }
   const uint32_t words = (L.n + 31) >> 5;
   const uint32_t w0 = task.start >> 5;
-  for (uint32_t i = w0 + threadIdx.x; i < min(words, w0 + (uint32_t)(kChunk >> 5)); i += kScanThreads)
+  for (uint32_t i = w0 + threadIdx.x; i < min(words, w0 + (prm.chunk >> 5)); i += kScanThreads)
     L.mask[i] = __ldcg(mask1 + i);
 }
 
@@ -764,7 +785,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   const uint32_t n = L.n;
   const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
   constexpr int kWarps = kScanThreads / 32;
-  constexpr int kTrips = kChunk / kGroup / kWarps;
+  const int kTrips = (int)prm.chunk / kGroup / kWarps;
 #pragma unroll 1
   for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
     float4 gv[kBatch];
@@ -789,7 +810,8 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       const uint32_t nib_m1 = (m1w[u] >> (4 * (lane & 7))) & 0xFu;
       const uint32_t nib_old = (oldw[u] >> (4 * (lane & 7))) & 0xFu;
       const float gs4[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-      uint32_t nib2 = 0;
+      uint32_t nib2 = 0, nibc = 0;
+      uint32_t keys[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const bool contender = (e0 + c < n) && !((nib_m1 >> c) & 1u);
@@ -798,25 +820,20 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
           key = grow_key(gs4[c], grow_signed);
           bin = key >> kBinShift;
         }
-        const bool is_cand = contender && bin == bucket;
-        const bool grown = contender && bin > bucket;
-        if (grown) {
-          nib2 |= 1u << c;
-          if (!((nib_old >> c) & 1u) || prm.reinit_when_same) apply_new_connection(L, prm, e0 + c, gs4[c]);
-        }
-        const uint32_t cm = __ballot_sync(0xffffffffu, is_cand);
-        if (cm) {
-          uint32_t pos = 0;
-          const int leader = __ffs(cm) - 1;
-          if (lane == leader)
-            pos = kV3 ? atomicAdd(&s_cand, (uint32_t)__popc(cm)) : atomicAdd(&st->cand_cnt_grow, (uint32_t)__popc(cm));
-          pos = __shfl_sync(0xffffffffu, pos, leader);
-          if (is_cand) {
-            cand[pos + __popc(cm & ((1u << lane) - 1u))] = make_uint2(key, e0 + c);
-            atomicAdd(&hist2[(key >> 8) & 0xFFFu], 1u);
-          }
-        }
+        keys[c] = key;
+        if (contender && bin == bucket) nibc |= 1u << c;
+        if (contender && bin > bucket) nib2 |= 1u << c;
       }
+      // re-initialise the definitely grown connections: each lane walks its own set bits (usually 0 or 1 of 4), so the
+      // warp runs the body ~1.5 times per group instead of once per element column
+      uint32_t todo = prm.reinit_when_same ? nib2 : (nib2 & ~nib_old);
+      while (todo) {
+        const int c = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float gc = c == 0 ? gv[u].x : (c == 1 ? gv[u].y : (c == 2 ? gv[u].z : gv[u].w));
+        apply_new_connection(L, prm, e0 + c, gc);
+      }
+      append_cands<kV3>(nibc, keys, e0, lane, cand, kV3 ? &s_cand : &st->cand_cnt_grow, hist2);
       const uint32_t word2 = combine_nibbles(nib2, lane);
       if ((lane & 7) == 0 && word2) mask1[widx] = m1w[u] | word2;
     }
@@ -845,6 +862,7 @@ struct rigl_mask_plan {
   size_t zero_bytes = 0;   // leading region memset to 0 each run (states + histograms + per-block counts)
   size_t state_off = 0;
   size_t task_cnt_off = 0; // [2][n_blocks] candidates per scan block (drop, grow)
+  int chunk = rigl::kChunk; // elements per scan block
 };
 
 using namespace rigl;
@@ -855,6 +873,9 @@ extern "C" int64_t rigl_mask_words(int64_t n) { return n <= 0 ? 0 : ((n + 127) /
 
 extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers, rigl_mask_plan** out) {
   RIGL_REQUIRE(layers && out && n_layers > 0, "rigl_mask_plan_create: bad arguments");
+  int64_t chunk = kChunk;
+  if (const char* e = getenv("RIGL_MASK_CHUNK")) chunk = atoll(e);
+  RIGL_REQUIRE(chunk >= 4096 && chunk <= (1 << 20) && chunk % 4096 == 0, "RIGL_MASK_CHUNK must be a multiple of 4096");
   std::vector<LayerDev> host(n_layers);
   std::vector<BlockTask> tasks;
   size_t off = 0;
@@ -871,7 +892,7 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
   size_t total_tasks = 0;
   for (int l = 0; l < n_layers; ++l) {
     RIGL_REQUIRE(layers[l].n >= 1 && layers[l].n < (1ll << 31), "layer %d: n=%lld out of range", l, (long long)layers[l].n);
-    total_tasks += (size_t)((layers[l].n + kChunk - 1) / kChunk);
+    total_tasks += (size_t)((layers[l].n + chunk - 1) / chunk);
   }
   const size_t task_cnt_off = off;
   off += align_up(2 * total_tasks * sizeof(uint32_t), 256);
@@ -895,7 +916,7 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
     L.off_mask1 = off;
     off += align_up((size_t)rigl_mask_words(d.n) * 4, 256);
     L.first_task = (uint32_t)tasks.size();
-    for (int64_t s = 0; s < d.n; s += kChunk) tasks.push_back({(uint32_t)l, (uint32_t)s});
+    for (int64_t s = 0; s < d.n; s += chunk) tasks.push_back({(uint32_t)l, (uint32_t)s});
     L.n_tasks = (uint32_t)tasks.size() - L.first_task;
   }
   for (int l = 0; l < n_layers; ++l) {
@@ -909,6 +930,7 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
   p->zero_bytes = zero_bytes;
   p->state_off = state_off;
   p->task_cnt_off = task_cnt_off;
+  p->chunk = (int)chunk;
   cudaError_t e = cudaMalloc(&p->d_layers, sizeof(LayerDev) * n_layers);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_tasks, sizeof(BlockTask) * tasks.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->d_layers, host.data(), sizeof(LayerDev) * n_layers, cudaMemcpyHostToDevice);
@@ -990,6 +1012,7 @@ static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm_, void*
   prm.force_wlo = g_mask_force_wlo;
   prm.off_task_cnt = plan->task_cnt_off;
   prm.n_blocks = (uint32_t)plan->n_blocks;
+  prm.chunk = (uint32_t)plan->chunk;
   return g_mask_variant == 3 ? mask_update_launch_v<true>(plan, prm, ws, stream)
                              : mask_update_launch_v<false>(plan, prm, ws, stream);
 }
@@ -997,7 +1020,7 @@ static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm_, void*
 extern "C" int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
                                     float grow_divisor, float acc_scale, int reinit_when_same,
                                     void* workspace, size_t workspace_bytes, void* stream_) {
-  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, 0.f, 0u, 0u, -1, 0ull, 0u};
+  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, 0.f, 0u, 0u, -1, 0ull, 0u, 0u};
   return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
 }
 
@@ -1006,14 +1029,14 @@ extern "C" int rigl_mask_update_run_noise(rigl_mask_plan* plan, float drop_fract
                                           float noise_std, uint64_t noise_seed, void* workspace,
                                           size_t workspace_bytes, void* stream_) {
   RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std,
-                (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u};
+                (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u, 0u};
   return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
 }
 
 extern "C" int rigl_mask_noise_fill(float* out, int64_t n, uint32_t layer_noise_key, float noise_std,
                                     uint64_t noise_seed, void* stream_) {
   RIGL_REQUIRE(out && n >= 1 && n < (1ll << 31) && noise_std >= 0.f, "rigl_mask_noise_fill: bad arguments");
-  RunParams prm{0.f, 0, 1.f, 0.f, 0, noise_std, (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u};
+  RunParams prm{0.f, 0, 1.f, 0.f, 0, noise_std, (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u, 0u};
   const unsigned blocks = (unsigned)((n + 1023) / 1024);
   k_noise_fill<<<blocks, 256, 0, (cudaStream_t)stream_>>>(out, (uint32_t)n, layer_noise_key, prm);
   RIGL_LAUNCH_CHECK("k_noise_fill");
