@@ -144,12 +144,6 @@ RIGL_API int rigl_mask_update_run_noise(rigl_mask_plan* plan, float drop_fractio
  * (tests and the CPU oracle consume it; the product path never materialises it). */
 RIGL_API int rigl_mask_noise_fill(float* out, int64_t n, uint32_t layer_noise_key, float noise_std,
                          uint64_t noise_seed, void* stream);
-/* Kernel variant of the update (process-wide; default 3, or env RIGL_MASK_VARIANT=2): 3 = block-private candidate
- * lists, grow histogram filled above a sampled floor (validated in-kernel, exact recount otherwise), grow cut applied
- * by the publish kernel; 2 = one candidate list per layer, full grow histogram.  Results are bit-identical.
- * force_grow_hist_floor >= 0 (tests) overrides the sampled floor, e.g. 4095 sends every layer through the recount. */
-RIGL_API int rigl_mask_update_set_variant(int variant, int force_grow_hist_floor);
-
 /* Copies 8 int32 per layer {n_ones, n_prune, n_keep, drop_candidates, grow_candidates,
  * drop_bucket, grow_bucket, 0} to host (synchronises the stream). */
 RIGL_API int rigl_mask_plan_read_stats(const rigl_mask_plan* plan, const void* workspace,

@@ -21,14 +21,21 @@
 //                      select is the fallback for huge tie groups); completes the
 //                      grow histogram; picks the grow threshold bin
 //   E  k_scan_grow   : definite grows -> mask2 bit, weight/slot re-init at new
-//                      connections; threshold bin -> candidates
-//   F  k_resolve<1>  : exact grow cut (ORs the selected candidates into mask1)
-//   G  k_publish_mask: mask = mask1 | mask2, whole grid
+//                      connections; threshold bin -> block-private candidate lists
+//   F  k_resolve<1>  : exact grow cut (a 52-bit threshold per layer)
+//   G  k_publish_mask: every scan block applies the cut to its own candidate list
+//                      (bit + re-init), then mask = mask1 | mask2 for its chunk
 // Selection is by exact integer comparison of (key, index) composites, hence
 // deterministic and independent of atomic ordering.
 //
 // HBM traffic (algorithmic floor 8.25 N bytes): A reads 4N (+N/8),
-// C reads 8N, E reads 4N (+bitmaps) => ~16.4 N with no noise tensor.
+// C reads 8N, E reads 4N (+bitmaps) => ~16.4 N with no noise tensor.  The three scans
+// (A, C, E) are NOT HBM-bound: ~2 warp instructions per element at 0.4 IPC per
+// scheduler, and a block's duration is its dependent chain of load -> classify trips,
+// so the scan block is small (8192 elements: ~5 waves instead of 1.3 of 4x longer
+// blocks; measured 0.36 -> 0.30 ms for the sequence).  Cutting the shared-memory
+// histogram atomics 8x (a sampled floor under the grow threshold, validated in-kernel)
+// was built and measured: 125 -> 112 us for C, paid back by the sampling -- not kept.
 #include <cstdlib>
 #include <vector>
 
@@ -41,7 +48,7 @@ constexpr int kBinShift = 20;
 constexpr uint32_t kKeyZero = 0x80000000u;  // ord_key(+0.0f)
 constexpr int kScanThreads = 256;
 constexpr int kGroup = 128;                 // elements per warp-iteration (float4 per lane)
-constexpr int kChunk = 32768;               // default elements per scan block (plan->chunk; RIGL_MASK_CHUNK)
+constexpr int kChunk = 8192;                // default elements per scan block (plan->chunk; env RIGL_MASK_CHUNK)
 constexpr int kResolveThreads = 1024;
 constexpr int kRBins = 2048;
 constexpr int kBatch = 2;                   // groups whose loads are issued together per trip
@@ -51,7 +58,7 @@ struct LayerState {     // 64 bytes, zeroed at the start of every run
   int32_t n_cand_grow, drop_bucket, grow_bucket, n_ones_acc;
   uint32_t drop_need, grow_need, cand_cnt_drop, cand_cnt_grow;
   int32_t n_grow;          // connections to grow: n_prune, or 0 with RIGL_LAYER_DROP_ONLY
-  uint32_t grow_wlo;       // lowest bin of the grow histogram that k_scan_drop fills (0 = all of it)
+  uint32_t pad1;
   uint32_t grow_thresh_lo, grow_thresh_hi;   // exact grow cut (52-bit composite), applied by k_publish_mask
 };
 
@@ -93,8 +100,7 @@ struct RunParams {
   int reinit_when_same;
   float noise_std;            // > 0: layers without a noise tensor draw N(0, noise_std) in-kernel
   uint32_t seed_lo, seed_hi;  // run key of that draw (seed offset + hash | global step)
-  int force_wlo;              // >= 0: test knob, overrides the sampled lower bound of the grow histogram
-  uint64_t off_task_cnt;      // workspace offset of the per-block candidate counts: [2][n_blocks] (drop, grow)
+  uint64_t off_task_cnt;      // workspace offset of the grow candidates per scan block: [n_blocks]
   uint32_t n_blocks;
   uint32_t chunk;             // elements per scan block (a multiple of 4096)
 };
@@ -316,17 +322,12 @@ __device__ __forceinline__ void find_bin_desc(const uint32_t* hist, uint32_t nee
 // ----------------------------------------------------------------------------
 // B: per-layer counts and drop threshold bin
 // ----------------------------------------------------------------------------
-constexpr uint32_t kSampleMinN = 131072;   // smaller layers fill the whole grow histogram (cheap anyway)
-constexpr int kSamplesPerThread = 4;           // 4096 sampled positions per layer
-
-template <bool kV3>
 __global__ void __launch_bounds__(kResolveThreads)
 k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t out[3];
-  __shared__ int32_t s_counts[4];
-  __shared__ uint32_t s_sampled;
+  __shared__ int32_t s_counts[2];
   const LayerDev L = layers[blockIdx.x];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   const uint32_t* gh = reinterpret_cast<const uint32_t*>(ws + L.off_hist_drop);
@@ -342,8 +343,6 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     if (n_prune < 0) n_prune = 0;
     s_counts[0] = n_ones - n_prune;
     s_counts[1] = n_prune;
-    s_counts[2] = (L.flags & RIGL_LAYER_DROP_ONLY) ? 0 : n_prune;
-    s_counts[3] = (int32_t)L.n - n_ones;            // inactive positions: grow contenders whatever is dropped
     st->n_ones = n_ones;
     st->n_prune = n_prune;
     st->n_keep = n_ones - n_prune;
@@ -358,56 +357,11 @@ k_pick_drop(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     st->drop_need = out[1];
     st->n_cand_drop = (int32_t)out[2];
   }
-  if (!kV3) return;
-  // Lower bound of the grow histogram.  k_scan_drop pays a shared-memory atomic (2 clk per lane on sm_100) for every
-  // grow contender it bins, and only the top n_grow of them (a few %) decide the threshold bin: bins below a bound
-  // `wlo` that surely lies under that bin are not filled.  The bound is the bin of the r-th largest |grad| among
-  // ~4096 sampled INACTIVE positions, r = the expected number of sampled contenders above the cut + 6 sigma
-  // (connections dropped by this update only add contenders above any bound: the error is on the safe side).
-  // It never decides the result: k_resolve<drop> checks that the filled bins hold >= n_grow contenders and
-  // otherwise recounts the layer exactly.
-  __syncthreads();
-  uint32_t wlo = 0;
-  const int32_t n_grow = s_counts[2], n_inactive = s_counts[3];
-  if (prm.force_wlo >= 0) {
-    wlo = (uint32_t)prm.force_wlo;
-  } else if (n_grow > 0 && n_inactive > 0 && L.n >= kSampleMinN) {
-    for (int b = threadIdx.x; b < kBins; b += kResolveThreads) hist[b] = 0;
-    if (threadIdx.x == 0) { s_sampled = 0; out[0] = 0; }
-    __syncthreads();
-    const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
-    uint32_t pos[kSamplesPerThread], bit[kSamplesPerThread];
-    float gs[kSamplesPerThread];
-#pragma unroll
-    for (int u = 0; u < kSamplesPerThread; ++u) {
-      const uint32_t j = (uint32_t)threadIdx.x + (uint32_t)u * kResolveThreads;
-      pos[u] = (uint32_t)(((uint64_t)(j * 2654435761u) * (uint64_t)L.n) >> 32);     // hashed: no stride to alias with
-      bit[u] = (__ldg(L.mask + (pos[u] >> 5)) >> (pos[u] & 31)) & 1u;
-      gs[u] = __ldg(L.g + pos[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < kSamplesPerThread; ++u) {
-      if (!bit[u]) {
-        atomicAdd(&hist[grow_key(gs[u], grow_signed) >> kBinShift], 1u);
-        atomicAdd(&s_sampled, 1u);
-      }
-    }
-    __syncthreads();
-    const float s0 = (float)s_sampled;
-    const float p = fminf(1.f, (float)n_grow / (float)n_inactive);
-    const float r = s0 * p + 6.f * sqrtf(s0 * p * (1.f - p)) + 8.f;
-    if (r < s0) {                                        // block-uniform
-      find_bin_desc<kBins>(hist, (uint32_t)r, warp_sums, out);
-      wlo = out[0];
-    }
-  }
-  if (threadIdx.x == 0) st->grow_wlo = wlo;
 }
 
 // Appends one warp's candidates of a 128-element group to a candidate list: lane holds up to four (bit c of nibc set
 // <=> element e0 + c, key keys[c]).  One warp scan + ONE counter atomic per group (instead of a ballot, an atomic and a
 // shuffle per element column); the order inside the list is irrelevant to the selection.
-template <bool kShared>
 __device__ __forceinline__ void append_cands(uint32_t nibc, const uint32_t (&keys)[4], uint32_t e0, int lane,
                                              uint2* __restrict__ cand, uint32_t* counter, uint32_t* __restrict__ hist2) {
   if (!__any_sync(0xffffffffu, nibc != 0u)) return;
@@ -419,7 +373,7 @@ __device__ __forceinline__ void append_cands(uint32_t nibc, const uint32_t (&key
     if (lane >= o) incl += t;
   }
   uint32_t base = 0;
-  if (lane == 31) base = atomicAdd(counter, incl);     // shared-memory (block-private list) or global (layer list)
+  if (lane == 31) base = atomicAdd(counter, incl);     // global (one list per layer) or shared (block-private list)
   base = __shfl_sync(0xffffffffu, base, 31);
   uint32_t pos = base + incl - mine;
 #pragma unroll
@@ -434,26 +388,20 @@ __device__ __forceinline__ void append_cands(uint32_t nibc, const uint32_t (&key
 // ----------------------------------------------------------------------------
 // C: classify against the drop threshold bin, build mask1, grow histogram
 // ----------------------------------------------------------------------------
-// kV3: (i) candidates go to a block-private list (cand + task.start, at most kChunk entries; the position comes from
-// a shared-memory counter, the per-block count goes to task_cnt[]) instead of one list per layer whose tail is a
-// single global atomic that every warp of the layer waits ~0.5 us for; (ii) the grow histogram is filled from bin
-// `grow_wlo` upwards only (see k_pick_drop).
-template <bool kGenNoise, bool kV3>
+// (drop candidates are rare -- the threshold bin of the ~20 % active weights -- and go to ONE list per layer)
+template <bool kGenNoise>
 __global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t hist[kBins];
-  __shared__ uint32_t s_cand;
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
   uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + L.off_hist2_drop);
-  uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand) + (kV3 ? task.start : 0u);
+  uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand);
   for (int b = threadIdx.x; b < kBins; b += kScanThreads) hist[b] = 0;
-  if (threadIdx.x == 0) s_cand = 0;
   __syncthreads();
   const uint32_t bucket = (uint32_t)st->drop_bucket;
-  const uint32_t wlo = kV3 ? st->grow_wlo : 0u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool explicit_score = L.sdrop != nullptr;
   const bool gen_noise = kGenNoise && L.noise == nullptr && !explicit_score && prm.noise_std > 0.f;
@@ -510,24 +458,19 @@ k_scan_drop(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
         if (valid && !kept && !is_cand) {          // definitely dropped / inactive: a grow contender
           const uint32_t gkey = grow_key(gs4[c], grow_signed);
           if (gkey == kKeyZero) ++zero_cnt;
-          else if (!kV3 || (gkey >> kBinShift) >= wlo) atomicAdd(&hist[gkey >> kBinShift], 1u);
+          else atomicAdd(&hist[gkey >> kBinShift], 1u);
         }
       }
-      append_cands<kV3>(nibc, keys, e0, lane, cand, kV3 ? &s_cand : &st->cand_cnt_drop, hist2);
+      append_cands(nibc, keys, e0, lane, cand, &st->cand_cnt_drop, hist2);
       const uint32_t word = combine_nibbles(nib1, lane);
       if ((lane & 7) == 0) mask1[(bases[u] >> 5) + (lane >> 3)] = word;
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) zero_cnt += __shfl_xor_sync(0xffffffffu, zero_cnt, o);
-  if (lane == 0 && zero_cnt && (kKeyZero >> kBinShift) >= wlo) atomicAdd(&hist[kKeyZero >> kBinShift], zero_cnt);
+  if (lane == 0 && zero_cnt) atomicAdd(&hist[kKeyZero >> kBinShift], zero_cnt);
   __syncthreads();
   flush_hist(hist, reinterpret_cast<uint32_t*>(ws + L.off_hist_grow));
-  if (kV3 && threadIdx.x == 0) {
-    const uint32_t c = s_cand;
-    reinterpret_cast<uint32_t*>(ws + prm.off_task_cnt)[blockIdx.x] = c;
-    if (c) atomicAdd(&st->cand_cnt_drop, c);
-  }
 }
 
 // ----------------------------------------------------------------------------
@@ -560,13 +503,13 @@ __device__ __forceinline__ uint64_t composite(uint2 c) {
 
 constexpr int kSubCap = 1024;      // sub-candidates ranked exactly in shared memory
 
-// Visits every candidate of a layer with the whole block.  One list per layer (cnt entries), or, kV3, one list per
-// scan block (blk_cnt[b] entries at cand + b * kChunk): a warp per list, lanes striding over it.
-template <bool kV3, typename F>
+// Visits every candidate of a layer with the whole block.  One list per layer (cnt entries: drop), or one list per
+// scan block (blk_cnt[b] entries at cand + b * chunk: grow) -- a warp per list, lanes striding over it.
+template <bool kLists, typename F>
 __device__ __forceinline__ void for_each_cand(const uint2* __restrict__ cand, uint32_t cnt,
                                               const uint32_t* __restrict__ blk_cnt, uint32_t n_lists, uint32_t chunk,
                                               F&& f) {
-  if (!kV3) {
+  if (!kLists) {
     for (uint32_t i = threadIdx.x; i < cnt; i += kResolveThreads) f(cand[i]);
   } else {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -578,7 +521,7 @@ __device__ __forceinline__ void for_each_cand(const uint2* __restrict__ cand, ui
   }
 }
 
-template <bool kGrow, bool kV3>
+template <bool kGrow>
 __global__ void __launch_bounds__(kResolveThreads)
 k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   __shared__ uint32_t h2[kBins];                 // level-2 histogram; reused as the fallback radix histogram
@@ -595,8 +538,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   const uint32_t cnt = kGrow ? st->cand_cnt_grow : st->cand_cnt_drop;
   uint32_t need = kGrow ? st->grow_need : st->drop_need;
   const int tid = threadIdx.x;
-  const uint32_t* blk_cnt = reinterpret_cast<const uint32_t*>(ws + prm.off_task_cnt) + (kGrow ? prm.n_blocks : 0u) +
-                            L.first_task;
+  const uint32_t* blk_cnt = reinterpret_cast<const uint32_t*>(ws + prm.off_task_cnt) + L.first_task;   // (grow)
 
   {
     const uint32_t* g2 = reinterpret_cast<const uint32_t*>(ws + (kGrow ? L.off_hist2_grow : L.off_hist2_drop));
@@ -621,7 +563,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
     thresh = (uint64_t)b2 << 40;
     if (in_bin != need) {
       // gather the elements of the level-2 threshold bin
-      for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
+      for_each_cand<kGrow>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
         if (((c.x >> 8) & 0xFFFu) == b2) {
           const uint32_t pos = atomicAdd(&sub_cnt, 1u);
           if (pos < (uint32_t)kSubCap) sub[pos] = c;
@@ -649,7 +591,7 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
           const int sh = shifts[p], wd = widths[p];
           for (int b = tid; b < kRBins; b += kResolveThreads) h2[b] = 0;
           __syncthreads();
-          for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 cc) {
+          for_each_cand<kGrow>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 cc) {
             const uint64_t c = composite(cc);
             if ((c >> (sh + wd)) == prefix) atomicAdd(&h2[(uint32_t)(c >> sh) & ((1u << wd) - 1u)], 1u);
           });
@@ -667,52 +609,22 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
   }
   __syncthreads();
 
-  // --- act on the candidates ---
-  if (kGrow && kV3) {
-    // the cut is applied by k_publish_mask, every scan block to its own list
+  if constexpr (kGrow) {
+    // the grow cut is applied by k_publish_mask, every scan block to its own list (one block per layer walking
+    // ~40 k candidates and copying a 2.4 M-bit bitmap was most of this kernel's time)
     if (tid == 0) { st->grow_thresh_lo = (uint32_t)thresh; st->grow_thresh_hi = (uint32_t)(thresh >> 32); }
-    return;
-  }
-  for_each_cand<kV3>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
-    const bool sel = composite(c) >= thresh;
-    const uint32_t e = c.y;
-    if (sel) {
-      atomicOr(mask1 + (e >> 5), 1u << (e & 31));
-      if (kGrow) {
-        const bool was_on = (__ldg(L.mask + (e >> 5)) >> (e & 31)) & 1u;
-        if (!was_on || prm.reinit_when_same) apply_new_connection(L, prm, e, __ldg(L.g + e));
+  } else {
+    // --- act on the drop candidates: kept -> mask1 bit; dropped -> a grow contender ---
+    for_each_cand<false>(cand, cnt, blk_cnt, L.n_tasks, prm.chunk, [&](const uint2 c) {
+      const uint32_t e = c.y;
+      if (composite(c) >= thresh) {
+        atomicOr(mask1 + (e >> 5), 1u << (e & 31));
+      } else {
+        const uint32_t gkey = grow_key(__ldg(L.g + e), (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0);
+        atomicAdd(&ghist[gkey >> kBinShift], 1u);
       }
-    } else if (!kGrow) {
-      const uint32_t gkey = grow_key(__ldg(L.g + e), (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0);
-      atomicAdd(&ghist[gkey >> kBinShift], 1u);
-    }
-  });
-  __syncthreads();
-
-  if (!kGrow) {
-    const uint32_t wlo = kV3 ? st->grow_wlo : 0u;
-    if (kV3 && wlo > 0 && st->n_grow > 0) {
-      // k_scan_drop filled the grow histogram from bin wlo upwards only: valid iff those bins hold the top n_grow
-      uint32_t part = 0;
-      for (int b = tid; b < kBins; b += kResolveThreads) part += ((uint32_t)b >= wlo) ? ghist[b] : 0u;
-      const uint32_t incl = block_inclusive_scan(part, warp_sums);
-      if (tid == kResolveThreads - 1) out[0] = incl;
-      __syncthreads();
-      const bool enough = out[0] >= (uint32_t)st->n_grow;
-      __syncthreads();
-      if (!enough) {
-        // the sampled bound was too high (or forced by the test knob): recount this layer exactly -- every position
-        // whose mask1 bit is clear is a contender (kept and selected-candidate bits were set above)
-        for (int b = tid; b < kBins; b += kResolveThreads) ghist[b] = 0;
-        __syncthreads();
-        const bool grow_signed = (L.flags & RIGL_LAYER_GROW_SCORE_SIGNED) != 0;
-        for (uint32_t e = tid; e < L.n; e += kResolveThreads) {
-          if (!((__ldcg(mask1 + (e >> 5)) >> (e & 31)) & 1u))
-            atomicAdd(&ghist[grow_key(__ldg(L.g + e), grow_signed) >> kBinShift], 1u);
-        }
-        __syncthreads();
-      }
-    }
+    });
+    __syncthreads();
     // grow threshold bin: top-n_prune among positions with mask1 == 0
     if (tid == 0) { out[0] = kBins; out[1] = 0; out[2] = 0; }
     __syncthreads();
@@ -724,23 +636,20 @@ k_resolve(const LayerDev* __restrict__ layers, uint8_t* ws, RunParams prm) {
       st->n_cand_grow = (int32_t)out[2];
     }
   }
-  // (grow: the final bitmap mask1 | mask2 is published by k_publish_mask over the whole grid -- one block per layer
-  //  copying a 2.4 M-bit bitmap was a third of this kernel's time)
 }
 
-// G: mask <- mask1 (| mask2, already OR-ed in by k_scan_grow / k_resolve<grow>), all layers, full grid
-// kV3: first applies the exact grow cut to this block's own candidate list (every candidate of the list lies in this
-// block's chunk of the bitmap, so the OR-ed bits are complete before the copy below).
-template <bool kV3>
+// G: applies the exact grow cut to this block's own candidate list (bit into mask1 + re-initialisation; every
+// candidate of the list lies in this block's chunk of the bitmap, so the OR-ed bits are complete before the copy),
+// then mask <- mask1 (| mask2, already OR-ed in by k_scan_grow) for the chunk.  All layers, full grid.
 __global__ void __launch_bounds__(kScanThreads)
 k_publish_mask(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws,
                RunParams prm) {
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
-  if (kV3) {
+  {
     const LayerState* st = reinterpret_cast<const LayerState*>(ws + L.off_state);
-    const uint32_t c = reinterpret_cast<const uint32_t*>(ws + prm.off_task_cnt)[prm.n_blocks + blockIdx.x];
+    const uint32_t c = reinterpret_cast<const uint32_t*>(ws + prm.off_task_cnt)[blockIdx.x];
     if (c > 0 && st->n_grow > 0) {
       const uint64_t thresh = ((uint64_t)st->grow_thresh_hi << 32) | (uint64_t)st->grow_thresh_lo;
       const uint2* lst = reinterpret_cast<const uint2*>(ws + L.off_cand) + task.start;
@@ -765,18 +674,20 @@ k_publish_mask(const LayerDev* __restrict__ layers, const BlockTask* __restrict_
 // ----------------------------------------------------------------------------
 // E: classify against the grow threshold bin
 // ----------------------------------------------------------------------------
-template <bool kV3>
+// Grow candidates (a few % of ALL positions) go to a block-private list: cand + task.start, at most `chunk` entries,
+// the position from a shared-memory counter, the per-block count to task_cnt[] -- one list per layer would hang every
+// group of every warp of the layer on the round trip of one global atomic (measured: 99 vs 71 us for this kernel).
 __global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws,
             RunParams prm) {
   __shared__ uint32_t s_cand;
-  constexpr int kBatch = kV3 ? 4 : rigl::kBatch;      // loads of 4 groups in flight (this scan holds few registers)
+  constexpr int kBatch = 4;                           // loads of 4 groups in flight (this scan holds few registers)
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
   uint32_t* mask1 = reinterpret_cast<uint32_t*>(ws + L.off_mask1);
   uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + L.off_hist2_grow);
-  uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand) + (kV3 ? task.start : 0u);
+  uint2* cand = reinterpret_cast<uint2*>(ws + L.off_cand) + task.start;
   if (st->n_grow == 0) return;                        // nothing grows; mask1 is final (block-uniform exit)
   if (threadIdx.x == 0) s_cand = 0;
   __syncthreads();
@@ -833,18 +744,16 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
         const float gc = c == 0 ? gv[u].x : (c == 1 ? gv[u].y : (c == 2 ? gv[u].z : gv[u].w));
         apply_new_connection(L, prm, e0 + c, gc);
       }
-      append_cands<kV3>(nibc, keys, e0, lane, cand, kV3 ? &s_cand : &st->cand_cnt_grow, hist2);
+      append_cands(nibc, keys, e0, lane, cand, &s_cand, hist2);
       const uint32_t word2 = combine_nibbles(nib2, lane);
       if ((lane & 7) == 0 && word2) mask1[widx] = m1w[u] | word2;
     }
   }
-  if (kV3) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t c = s_cand;
-      reinterpret_cast<uint32_t*>(ws + prm.off_task_cnt)[prm.n_blocks + blockIdx.x] = c;
-      if (c) atomicAdd(&st->cand_cnt_grow, c);
-    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t c = s_cand;
+    reinterpret_cast<uint32_t*>(ws + prm.off_task_cnt)[blockIdx.x] = c;
+    if (c) atomicAdd(&st->cand_cnt_grow, c);
   }
 }
 
@@ -861,7 +770,7 @@ struct rigl_mask_plan {
   size_t ws_bytes = 0;
   size_t zero_bytes = 0;   // leading region memset to 0 each run (states + histograms + per-block counts)
   size_t state_off = 0;
-  size_t task_cnt_off = 0; // [2][n_blocks] candidates per scan block (drop, grow)
+  size_t task_cnt_off = 0; // [n_blocks] grow candidates per scan block
   int chunk = rigl::kChunk; // elements per scan block
 };
 
@@ -895,7 +804,7 @@ extern "C" int rigl_mask_plan_create(const rigl_layer_desc* layers, int n_layers
     total_tasks += (size_t)((layers[l].n + chunk - 1) / chunk);
   }
   const size_t task_cnt_off = off;
-  off += align_up(2 * total_tasks * sizeof(uint32_t), 256);
+  off += align_up(total_tasks * sizeof(uint32_t), 256);
   const size_t zero_bytes = off;
   for (int l = 0; l < n_layers; ++l) {
     const rigl_layer_desc& d = layers[l];
@@ -955,41 +864,6 @@ extern "C" size_t rigl_mask_plan_workspace_bytes(const rigl_mask_plan* plan) {
   return plan ? plan->ws_bytes : 0;
 }
 
-// Kernel variant: 3 = block-private candidate lists + sampled lower bound of the grow histogram + the grow cut
-// applied by the publish kernel; 2 = one candidate list per layer, full grow histogram (RIGL_MASK_VARIANT=2).
-static int g_mask_variant = -1;
-static int g_mask_force_wlo = -1;
-
-extern "C" int rigl_mask_update_set_variant(int variant, int force_grow_hist_floor) {
-  RIGL_REQUIRE(variant == 2 || variant == 3, "rigl_mask_update_set_variant: variant must be 2 or 3");
-  RIGL_REQUIRE(force_grow_hist_floor < kBins, "rigl_mask_update_set_variant: floor must be < %d", kBins);
-  g_mask_variant = variant;
-  g_mask_force_wlo = force_grow_hist_floor;
-  return RIGL_OK;
-}
-
-template <bool kV3>
-static int mask_update_launch_v(rigl_mask_plan* plan, const RunParams& prm, uint8_t* ws, cudaStream_t stream) {
-  const bool gen = prm.noise_std > 0.f;
-  if (gen) k_hist_drop<true><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  else k_hist_drop<false><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  RIGL_LAUNCH_CHECK("k_hist_drop");
-  k_pick_drop<kV3><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
-  RIGL_LAUNCH_CHECK("k_pick_drop");
-  if (gen) k_scan_drop<true, kV3><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  else k_scan_drop<false, kV3><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  RIGL_LAUNCH_CHECK("k_scan_drop");
-  k_resolve<false, kV3><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
-  RIGL_LAUNCH_CHECK("k_resolve<drop>");
-  k_scan_grow<kV3><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  RIGL_LAUNCH_CHECK("k_scan_grow");
-  k_resolve<true, kV3><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
-  RIGL_LAUNCH_CHECK("k_resolve<grow>");
-  k_publish_mask<kV3><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
-  RIGL_LAUNCH_CHECK("k_publish_mask");
-  return RIGL_OK;
-}
-
 static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm_, void* workspace, size_t workspace_bytes,
                               void* stream_) {
   RunParams prm = prm_;
@@ -1005,22 +879,33 @@ static int mask_update_launch(rigl_mask_plan* plan, const RunParams& prm_, void*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   RIGL_CUDA(cudaMemsetAsync(ws, 0, plan->zero_bytes, stream));
-  if (g_mask_variant < 0) {
-    const char* e = getenv("RIGL_MASK_VARIANT");
-    g_mask_variant = (e && e[0] == '2') ? 2 : 3;
-  }
-  prm.force_wlo = g_mask_force_wlo;
   prm.off_task_cnt = plan->task_cnt_off;
   prm.n_blocks = (uint32_t)plan->n_blocks;
   prm.chunk = (uint32_t)plan->chunk;
-  return g_mask_variant == 3 ? mask_update_launch_v<true>(plan, prm, ws, stream)
-                             : mask_update_launch_v<false>(plan, prm, ws, stream);
+  const bool gen = prm.noise_std > 0.f;
+  if (gen) k_hist_drop<true><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  else k_hist_drop<false><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  RIGL_LAUNCH_CHECK("k_hist_drop");
+  k_pick_drop<<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
+  RIGL_LAUNCH_CHECK("k_pick_drop");
+  if (gen) k_scan_drop<true><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  else k_scan_drop<false><<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  RIGL_LAUNCH_CHECK("k_scan_drop");
+  k_resolve<false><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
+  RIGL_LAUNCH_CHECK("k_resolve<drop>");
+  k_scan_grow<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  RIGL_LAUNCH_CHECK("k_scan_grow");
+  k_resolve<true><<<plan->n_layers, kResolveThreads, 0, stream>>>(plan->d_layers, ws, prm);
+  RIGL_LAUNCH_CHECK("k_resolve<grow>");
+  k_publish_mask<<<plan->n_blocks, kScanThreads, 0, stream>>>(plan->d_layers, plan->d_tasks, ws, prm);
+  RIGL_LAUNCH_CHECK("k_publish_mask");
+  return RIGL_OK;
 }
 
 extern "C" int rigl_mask_update_run(rigl_mask_plan* plan, float drop_fraction, int grow_mode,
                                     float grow_divisor, float acc_scale, int reinit_when_same,
                                     void* workspace, size_t workspace_bytes, void* stream_) {
-  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, 0.f, 0u, 0u, -1, 0ull, 0u, 0u};
+  RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, 0.f, 0u, 0u, 0ull, 0u, 0u};
   return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
 }
 
@@ -1029,14 +914,14 @@ extern "C" int rigl_mask_update_run_noise(rigl_mask_plan* plan, float drop_fract
                                           float noise_std, uint64_t noise_seed, void* workspace,
                                           size_t workspace_bytes, void* stream_) {
   RunParams prm{drop_fraction, grow_mode, grow_divisor, acc_scale, reinit_when_same, noise_std,
-                (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u, 0u};
+                (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), 0ull, 0u, 0u};
   return mask_update_launch(plan, prm, workspace, workspace_bytes, stream_);
 }
 
 extern "C" int rigl_mask_noise_fill(float* out, int64_t n, uint32_t layer_noise_key, float noise_std,
                                     uint64_t noise_seed, void* stream_) {
   RIGL_REQUIRE(out && n >= 1 && n < (1ll << 31) && noise_std >= 0.f, "rigl_mask_noise_fill: bad arguments");
-  RunParams prm{0.f, 0, 1.f, 0.f, 0, noise_std, (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), -1, 0ull, 0u, 0u};
+  RunParams prm{0.f, 0, 1.f, 0.f, 0, noise_std, (uint32_t)(noise_seed & 0xffffffffu), (uint32_t)(noise_seed >> 32), 0ull, 0u, 0u};
   const unsigned blocks = (unsigned)((n + 1023) / 1024);
   k_noise_fill<<<blocks, 256, 0, (cudaStream_t)stream_>>>(out, (uint32_t)n, layer_noise_key, prm);
   RIGL_LAUNCH_CHECK("k_noise_fill");

@@ -13,18 +13,6 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-# Every test of this module runs on both kernel variants (include/rigl_b200.h: rigl_mask_update_set_variant) and,
-# for variant 3, with the floor of the grow histogram forced: 4095 sends every layer through the exact recount,
-# 3060 (|score| >= ~0.75) filters the histogram for unit-scale scores and is below / above everything for others.
-@pytest.fixture(autouse=True, params=[(3, -1), (2, -1), (3, 4095), (3, 3060)],
-                ids=['v3', 'v2', 'v3-recount', 'v3-floor3060'])
-def kernel_variant(request):
-  variant, floor = request.param
-  _cabi.check(_cabi.lib().rigl_mask_update_set_variant(variant, floor))
-  yield request.param
-  _cabi.check(_cabi.lib().rigl_mask_update_set_variant(3, -1))
-
-
 def _t(a):
   return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
 

@@ -43,9 +43,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--noise', action='store_true', help='drop-score noise read from a tensor')
   ap.add_argument('--inkernel-noise', action='store_true', help='drop-score noise drawn inside the kernels')
-  ap.add_argument('--variant', type=int, default=3, help='kernel variant (rigl_mask_update_set_variant): 2 or 3')
   args = ap.parse_args()
-  _cabi.check(_cabi.lib().rigl_mask_update_set_variant(args.variant, -1))
   specs = build_layers(args.tag, args.noise)
   total_n = sum(s['mask'].size for s in specs)
   eng = MaskUpdateEngine()
@@ -67,7 +65,7 @@ def main():
   ms = float(np.median(times))
   alg_bytes = (8.25 + (4 if args.noise else 0)) * total_n
   print(json.dumps({'bench': 'mask_update', 'tag': args.tag, 'layers': len(specs), 'weights': total_n,
-                    'variant': args.variant, 'noise': args.noise, 'inkernel_noise': args.inkernel_noise, 'ms_median': ms, 'ms_min': float(min(times)),
+                    'scan_block': int(os.environ.get('RIGL_MASK_CHUNK', 8192)), 'noise': args.noise, 'inkernel_noise': args.inkernel_noise, 'ms_median': ms, 'ms_min': float(min(times)),
                     'algorithmic_GBps': alg_bytes / ms / 1e6, 'workspace_MB': eng.workspace_bytes / 2 ** 20,
                     'max_drop_candidates': max(s[3] for s in stats),
                     'max_grow_candidates': max(s[4] for s in stats),
