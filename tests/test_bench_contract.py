@@ -50,3 +50,18 @@ def test_product_arm_refuses_to_run_without_a_gpu():
   r = _run(['--steps', '1', '--warmup', '0', '--no-cpu-baseline'], timeout=300)
   assert r.returncode != 0, 'bench.py must not fall back to a CPU path'
   assert r.stdout.strip() == '', 'and must not print a bench line'
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+  # the driver launches the reference arm like the product arm (torchrun, N ranks): rank 0 alone measures and prints
+  env = dict(os.environ)
+  r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                      '--master-addr', '127.0.0.1', '--master-port', '29541', os.path.join(ROOT, 'bench.py'),
+                      '--impl', 'reference', '--config', 'c5', '--gpus', '2', '--steps', '2', '--warmup', '1'],
+                     cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+  assert r.returncode == 0, r.stderr[-2000:]
+  lines = [l for l in r.stdout.splitlines() if l.strip().startswith('{')]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
+  assert d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
