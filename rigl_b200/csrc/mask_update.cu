@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(kScanThreads, 4)
 k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ tasks, uint8_t* ws,
             RunParams prm) {
   __shared__ uint32_t s_cand;
-  constexpr int kBatch = 4;                           // loads of 4 groups in flight (this scan holds few registers)
+  constexpr int kGrowBatch = 4;                       // loads of 4 groups in flight (this scan holds few registers)
   const BlockTask task = tasks[blockIdx.x];
   const LayerDev L = layers[task.layer];
   LayerState* st = reinterpret_cast<LayerState*>(ws + L.off_state);
@@ -698,12 +698,12 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
   constexpr int kWarps = kScanThreads / 32;
   const int kTrips = (int)prm.chunk / kGroup / kWarps;
 #pragma unroll 1
-  for (int j0 = 0; j0 < kTrips; j0 += kBatch) {
-    float4 gv[kBatch];
-    uint32_t m1w[kBatch], oldw[kBatch], bases[kBatch];
-    bool act[kBatch];
+  for (int j0 = 0; j0 < kTrips; j0 += kGrowBatch) {
+    float4 gv[kGrowBatch];
+    uint32_t m1w[kGrowBatch], oldw[kGrowBatch], bases[kGrowBatch];
+    bool act[kGrowBatch];
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
+    for (int u = 0; u < kGrowBatch; ++u) {
       bases[u] = task.start + (uint32_t)(warp + kWarps * (j0 + u)) * kGroup;
       act[u] = bases[u] < n;
       if (act[u]) {
@@ -714,7 +714,7 @@ k_scan_grow(const LayerDev* __restrict__ layers, const BlockTask* __restrict__ t
       }
     }
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
+    for (int u = 0; u < kGrowBatch; ++u) {
       if (!act[u]) continue;
       const uint32_t e0 = bases[u] + 4 * lane;
       const uint32_t widx = (bases[u] >> 5) + (lane >> 3);
